@@ -1,0 +1,240 @@
+/*
+ * lbm_b200.h -- C ABI of liblbm_b200.so, a B200-native (sm_100a) D3Q19 BGK
+ * Lattice-Boltzmann solver that is a drop-in for the *case interface* of
+ * Xinhuan-Imperial/Lattice-Boltzmann-Method-GPU.
+ *
+ * The reference has no library / FFI surface: its "API" is the sequence of
+ * file-scope functions each of its four programs calls from main()
+ * (bifurcation.cu:1177-1326):
+ *      geo_pre(); index_transform(); read_vel(); initialize();
+ *      loop { update<<<>>>; boundary_stream<<<>>>; swap; } calc_res(); outputSave(t);
+ * Every entry point below names the reference function it replaces
+ * (file:line into /root/reference; ldc = Lid_driven_cavity/ldc.cu,
+ * pos = Poiseulle_flow/Poiseulle.cu, bif = bifurcation/bifurcation.cu,
+ * cor = coronary_cfd/coronary.cu).
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success, a negative
+ *    lbm_status otherwise; lbm_last_error(h) gives the message.  No exceptions
+ *    cross the ABI.  One caller thread per handle; handles are independent.
+ *  - "Cartesian" arrays are int32/real [nz][ny][nx], x fastest (the order of
+ *    geo.txt, bif:50-61).  "Compact" arrays have NLATTICE entries in the
+ *    reference's own numbering (running count over z,y,x of geo != 0,
+ *    bif:241-252; for the LDC rule every node is stored, ldc:54).
+ *  - real = float (LBM_F32, the reference's precision) or double (LBM_F64).
+ *  - the library owns all device memory; the caller owns the host buffers it
+ *    passes in.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+typedef struct lbm_solver_s *lbm_handle;
+
+typedef enum {
+    LBM_OK = 0,
+    LBM_ERR_ARG = -1,     /* bad argument / descriptor */
+    LBM_ERR_STATE = -2,   /* call out of order (e.g. step before initialize) */
+    LBM_ERR_IO = -3,      /* file missing / short */
+    LBM_ERR_CUDA = -4,    /* a CUDA call failed */
+    LBM_ERR_NOMEM = -5,
+    LBM_ERR_NO_DEVICE = -6 /* no CUDA device: there is deliberately no CPU fallback */
+} lbm_status;
+
+/* which reference program's geometry / initial-state / boundary rules apply */
+typedef enum {
+    LBM_CASE_LDC = 0,          /* ldc:468-580  lid-driven cavity, labels 0 ghost,1 wall,2 lid,3 fluid, dense */
+    LBM_CASE_POISEUILLE = 1,   /* pos:52-382   circular pipe along y, analytic in/outlet velocity */
+    LBM_CASE_GEO_Y_INOUT = 2,  /* bif:36-427   geo.txt voxels, inlet y=1 (bc.txt velocity), outlet y=NY-2 (pressure) */
+    LBM_CASE_GEO_OPENINGS = 3  /* cor:31-350   geo.txt voxels, list of opening planes, constant BC speeds */
+} lbm_case_rule;
+
+typedef enum { LBM_F32 = 0, LBM_F64 = 1 } lbm_precision;
+
+/* distribution storage */
+typedef enum {
+    LBM_STORE_DENSE_AB = 0,  /* box-dense SoA, two buffers, fused pull step            */
+    LBM_STORE_DENSE_AA = 1,  /* box-dense SoA, ONE buffer, in-place AA-pattern streaming */
+    LBM_STORE_SPARSE_AB = 2  /* reference compact order (NLATTICE entries), run-segment indirect addressing, two buffers */
+} lbm_storage;
+
+/* arithmetic of the fused kernel */
+typedef enum {
+    LBM_MATH_FAST = 0,   /* FMA-contracted, reciprocal-multiply BGK (default, the measured path) */
+    LBM_MATH_STRICT = 1  /* the reference's expression order, no contraction: bit-identical to the CPU oracle */
+} lbm_math;
+
+/* boundary-condition kinds of the non-equilibrium extrapolation */
+typedef enum {
+    LBM_BC_NONE = 0,
+    LBM_BC_V = 1,  /* rho from the fluid neighbour, prescribed u   (ldc:391-456, pos:748-891, bif:950-1021, cor:795-942) */
+    LBM_BC_P = 2,  /* rho = 1, u from the fluid neighbour          (bif:877-948) */
+    LBM_BC_VP = 3  /* rho = 1, prescribed u                        (cor:716-792) */
+} lbm_bc_kind;
+
+typedef enum {
+    LBM_SRC_CONST = 0,        /* value                                        (ldc:378, cor:717) */
+    LBM_SRC_PARABOLA = 1,     /* value*(1-((i-cx)^2+(k-cz)^2)/R^2), R=cx=(NX-1)/2, cz=(NZ-1)/2  (pos:597) */
+    LBM_SRC_PLANE_INLET = 2,  /* inlet plane[i + k*NX] from bc.txt            (bif:650,951) */
+    LBM_SRC_PLANE_OUTLET = 3  /* outlet plane[i + k*NX]                       (bif:296-325) */
+} lbm_bc_source;
+
+/* one boundary label.  Direction set = { q : c_q[normal_axis] == normal_sign }. */
+typedef struct {
+    int32_t label;       /* node label the entry applies to (1..7) */
+    int32_t kind;        /* lbm_bc_kind */
+    int32_t normal_axis; /* 0 x, 1 y, 2 z */
+    int32_t normal_sign; /* +1 / -1: points from the boundary node into the fluid */
+    int32_t vel_axis;    /* axis of the prescribed velocity */
+    int32_t source;      /* lbm_bc_source */
+    int32_t pulsatile;   /* != 0: multiply by 1 + pulse_amp*sin(2 pi t / pulse_period), t = step index.
+                            No reference code exists for this (curved vessel/README.md:1): parity unpinned. */
+    int32_t reserved;
+    double value;        /* speed used by the boundary kernel, lattice units (pos:590, cor:717) */
+    double init_value;   /* speed `initialize` gives nodes of this label (cor:302-306); the reference
+                            computes the two with different float expressions, so both are carried */
+} lbm_bc_desc;
+
+/* one "opening plane" of the GEO_OPENINGS rule (cor:77-141): on plane
+ * axis=coord, inside the inclusive window [lo_a,hi_a]x[lo_b,hi_b] of the two
+ * in-plane axes (in x,y,z order), label += reps * min4(in-plane neighbours of flag) */
+typedef struct {
+    int32_t axis, coord, lo_a, hi_a, lo_b, hi_b, reps, reserved;
+} lbm_opening_rule;
+
+#define LBM_MAX_BC 8
+#define LBM_MAX_OPENINGS 8
+
+typedef struct {
+    int32_t struct_size; /* sizeof(lbm_case_desc), checked */
+    int32_t case_rule;   /* lbm_case_rule */
+    int32_t nx, ny, nz;  /* GLOBAL box, the reference's NX,NY,NZ (bif:19) */
+    int32_t precision;   /* lbm_precision */
+    int32_t storage;     /* lbm_storage */
+    int32_t math;        /* lbm_math */
+    int32_t device;      /* CUDA device ordinal */
+    int32_t geo_yfast;   /* geo.txt stored y-fastest (cor:45-56) instead of x-fastest (bif:50-61) */
+    /* z-slab decomposition (new; the reference is single-GPU): this handle owns
+     * global planes [z_begin, z_end); 0,nz for a single domain. */
+    int32_t z_begin, z_end;
+    int32_t n_bc, n_openings;
+    double tau;          /* ldc:55, pos:39, bif:434 */
+    double u_max;        /* LDC lid speed (ldc:52) / Poiseuille peak used by initialize (pos:44) */
+    double C_U, C_rho, CH; /* unit converters used by the writers (bif:20) */
+    double pulse_amp, pulse_period;
+    lbm_bc_desc bc[LBM_MAX_BC];
+    lbm_opening_rule openings[LBM_MAX_OPENINGS];
+    char geo_path[256];  /* "./geo.txt" (bif:49) */
+    char bc_path[256];   /* "./bc.txt"  (bif:294) */
+    char out_dir[256];   /* "./out"     (bif:15) */
+    char out_name[32];   /* "lid","pos","bif","coronary" (ldc:585, pos:906, bif:1097, cor:950) */
+} lbm_case_desc;
+
+/* Fill `d` with the constants hard-coded in the reference program for `rule`
+ * (SURVEY A.7): dims, tau, u_max, unit converters, BC table, paths, names. */
+int lbm_case_defaults(int32_t case_rule, lbm_case_desc *d);
+
+/* replaces the global malloc/cudaMalloc block of main() (bif:1185-1222) */
+int lbm_create(const lbm_case_desc *desc, lbm_handle *out);
+/* replaces the free/cudaFree block (bif:1294-1322) */
+int lbm_destroy(lbm_handle h);
+const char *lbm_last_error(lbm_handle h); /* h may be NULL: last create() error */
+
+/* Supply the binary voxel field from memory instead of geo_path (Cartesian,
+ * GLOBAL box; host pointer).  Optional. */
+int lbm_set_flag(lbm_handle h, const int32_t *flag_cartesian);
+
+/* geo_pre(): ldc:468-502, pos:52-254, bif:36-239, cor:31-260.  Reads geo_path
+ * unless lbm_set_flag was called (LDC / POISEUILLE masks are analytic).  Label
+ * stencil + outer-wall-neighbour marking run as CUDA kernels. */
+int lbm_geo_pre(lbm_handle h);
+
+/* index_transform(): pos:257-271, bif:241-252, cor:262-273.  GPU stream
+ * compaction (flag -> exclusive scan -> scatter).  *nlattice = stored nodes of
+ * the GLOBAL box when compact_offset/total were supplied, else of this slab. */
+int lbm_index_transform(lbm_handle h, int64_t *nlattice);
+/* multi-slab: stored-node count of the owned planes (call after geo_pre), then
+ * tell the handle the running offset of its slab and the global total, so that
+ * compact indices equal the single-domain z,y,x numbering. */
+int lbm_local_stored_count(lbm_handle h, int64_t *count);
+int lbm_set_compact_offset(lbm_handle h, int64_t offset, int64_t total);
+
+/* read_vel(): bif:255-327 (bc_path) -- or the planes directly (host, float[nz*nx] each, GLOBAL) */
+int lbm_read_vel(lbm_handle h);
+int lbm_set_bc_planes(lbm_handle h, const float *inlet_uy, const float *outlet_uy);
+
+/* initialize(): ldc:504-580, pos:273-382, bif:329-427, cor:277-350 */
+int lbm_initialize(lbm_handle h);
+
+/* n iterations of { update; boundary_stream; swap }: ldc:654-666, bif:1249-1257.
+ * Macroscopic moments (bif:592-595) are materialised on the last of the n steps. */
+int lbm_step(lbm_handle h, int32_t n);
+/* same, timed with CUDA events on the library's own stream (ms for the n steps) */
+int lbm_step_timed(lbm_handle h, int32_t n, float *elapsed_ms);
+int64_t lbm_step_count(lbm_handle h);
+/* number of kernels the library has launched on this handle so far */
+int64_t lbm_launch_count(lbm_handle h);
+
+typedef enum {
+    LBM_RES_VELSUM = 0, /* S = sum_i sqrt(ux^2+uy^2+uz^2) over all stored entries   (ldc:460-466,662; pos:895-901,996) */
+    LBM_RES_U2SUM = 1   /* sum of |u|^2 over fluid nodes of the trimmed box          (bif:1158-1175, cor:1013-1030) */
+} lbm_residual_kind;
+/* value of the reduction for the current moments (device reduction, double) */
+int lbm_residual(lbm_handle h, int32_t kind, double *value);
+
+/* copies of h_geo / h_index (Cartesian int32, this handle's owned planes
+ * [z_begin,z_end) ) */
+int lbm_get_geo(lbm_handle h, int32_t *geo_cartesian);
+int lbm_get_index(lbm_handle h, int32_t *index_cartesian);
+/* D2H of d_rho,d_ux,d_uy,d_uz (bif:1261-1264): compact order, entries of the
+ * owned planes only, `real` = handle precision, never-updated entries are 0.
+ * `first`/`count` receive the compact range written (may be NULL). */
+int lbm_get_fields(lbm_handle h, void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count);
+/* debug: the 19 populations "as if in d_scr after the swap", real[19][count], compact order */
+int lbm_debug_get_populations(lbm_handle h, void *f);
+int64_t lbm_num_fluid(lbm_handle h); /* fluid nodes owned by this handle */
+int64_t lbm_device_bytes(lbm_handle h);
+
+/* outputSave(t): ldc:582-610, pos:903-938, bif:1095-1156, cor:948-1011 --
+ * byte-compatible ASCII legacy VTK under out_dir.  Single-domain handles only. */
+int lbm_output_save(lbm_handle h, int32_t t);
+
+/* The reference main loops, including CONVERGENCE.log and the stdout lines:
+ *  fixed:    for i in 0..repeat inclusive, save every time_save      (bif:1246-1274, cor:1100-1132)
+ *  converge: while k<=max_it && tol_count<=stag_max, residual each step (ldc:653-685, pos:986-1019) */
+int lbm_run_fixed(lbm_handle h, int32_t repeat, int32_t time_save, int32_t write_files);
+int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max, int32_t time_save,
+                     int32_t write_files, int32_t *iterations, double *residual);
+
+/* ---- z-slab halo exchange: the 5 populations crossing each face ----
+ * side 0 = low-z face (sends q with c_z=-1, receives c_z=+1), side 1 = high-z.
+ * lbm_halo_buffers returns DEVICE pointers to the contiguous send / receive
+ * staging buffers of that side (5 * nx_pitch * ny reals) for the caller's
+ * transport (NCCL send/recv, or a peer GPU's kernel storing straight into it).
+ * lbm_step_begin .. lbm_step_end bracket one step:
+ *   begin: face planes computed first, send buffers packed (async on stream)
+ *   <caller exchanges send->recv buffers of neighbouring handles>
+ *   end:   received populations unpacked into the halo planes, buffers swap. */
+int lbm_halo_buffers(lbm_handle h, int32_t side, void **send_dev, void **recv_dev, size_t *bytes);
+#define LBM_STEP_MOMENTS 1 /* materialise rho,u on this step (bif:592-595) */
+#define LBM_STEP_VELSUM 2  /* also accumulate S = sum|u| for lbm_last_velsum (ldc:660-662) */
+int lbm_step_begin(lbm_handle h, int32_t flags);
+int lbm_step_end(lbm_handle h);
+/* S of the most recent step run with LBM_STEP_VELSUM (this slab's share) */
+int lbm_last_velsum(lbm_handle h, double *value);
+/* cudaStream_t of the handle as an opaque pointer (for event / NCCL interop) */
+void *lbm_stream(lbm_handle h);
+int lbm_sync(lbm_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,338 @@
+"""ctypes binding of liblbm_b200.so and a host-side mirror of the reference's case interface.
+
+The reference (Xinhuan-Imperial/Lattice-Boltzmann-Method-GPU) has no library API: each of its
+four programs calls, from main(), the file-scope functions
+
+    geo_pre(); index_transform(); read_vel(); initialize();
+    loop { update<<<>>>; boundary_stream<<<>>>; swap }   calc_res(); outputSave(t);
+
+(bifurcation/bifurcation.cu:1177-1326).  :class:`Case` keeps those names and that order, so a
+driver or a test written against it reads like the reference's main().  All compute happens in
+the CUDA library; there is no CPU fallback -- if the shared library is missing or no GPU is
+visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "liblbm_b200.so"
+
+# enums of include/lbm_b200.h
+CASE_LDC, CASE_POISEUILLE, CASE_GEO_Y_INOUT, CASE_GEO_OPENINGS = 0, 1, 2, 3
+F32, F64 = 0, 1
+STORE_DENSE_AB, STORE_DENSE_AA, STORE_SPARSE_AB = 0, 1, 2
+MATH_FAST, MATH_STRICT = 0, 1
+BC_NONE, BC_V, BC_P, BC_VP = 0, 1, 2, 3
+SRC_CONST, SRC_PARABOLA, SRC_PLANE_INLET, SRC_PLANE_OUTLET = 0, 1, 2, 3
+RES_VELSUM, RES_U2SUM = 0, 1
+STEP_MOMENTS, STEP_VELSUM = 1, 2
+MAX_BC, MAX_OPENINGS = 8, 8
+
+
+class BcDesc(C.Structure):
+    _fields_ = [
+        ("label", C.c_int32), ("kind", C.c_int32), ("normal_axis", C.c_int32), ("normal_sign", C.c_int32),
+        ("vel_axis", C.c_int32), ("source", C.c_int32), ("pulsatile", C.c_int32), ("reserved", C.c_int32),
+        ("value", C.c_double), ("init_value", C.c_double),
+    ]
+
+
+class OpeningRule(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("axis", "coord", "lo_a", "hi_a", "lo_b", "hi_b", "reps", "reserved")]
+
+
+class CaseDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("case_rule", C.c_int32),
+        ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+        ("precision", C.c_int32), ("storage", C.c_int32), ("math", C.c_int32), ("device", C.c_int32),
+        ("geo_yfast", C.c_int32), ("z_begin", C.c_int32), ("z_end", C.c_int32),
+        ("n_bc", C.c_int32), ("n_openings", C.c_int32),
+        ("tau", C.c_double), ("u_max", C.c_double),
+        ("C_U", C.c_double), ("C_rho", C.c_double), ("CH", C.c_double),
+        ("pulse_amp", C.c_double), ("pulse_period", C.c_double),
+        ("bc", BcDesc * MAX_BC), ("openings", OpeningRule * MAX_OPENINGS),
+        ("geo_path", C.c_char * 256), ("bc_path", C.c_char * 256), ("out_dir", C.c_char * 256),
+        ("out_name", C.c_char * 32),
+    ]
+
+
+class LbmError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"liblbm_b200 status {status}: {msg}")
+        self.status = status
+
+
+# every symbol include/lbm_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "lbm_case_defaults", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_set_flag", "lbm_geo_pre",
+    "lbm_index_transform", "lbm_local_stored_count", "lbm_set_compact_offset", "lbm_read_vel", "lbm_set_bc_planes",
+    "lbm_initialize", "lbm_step", "lbm_step_timed", "lbm_step_count", "lbm_launch_count", "lbm_residual",
+    "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
+    "lbm_device_bytes", "lbm_output_save", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
+    "lbm_step_begin", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"or `make -C {PKG / 'csrc'}`.  There is no CPU fallback.")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    sig = {
+        "lbm_case_defaults": ([i32, P(CaseDesc)], C.c_int),
+        "lbm_create": ([P(CaseDesc), P(vp)], C.c_int),
+        "lbm_destroy": ([vp], C.c_int),
+        "lbm_last_error": ([vp], C.c_char_p),
+        "lbm_set_flag": ([vp, vp], C.c_int),
+        "lbm_geo_pre": ([vp], C.c_int),
+        "lbm_index_transform": ([vp, P(i64)], C.c_int),
+        "lbm_local_stored_count": ([vp, P(i64)], C.c_int),
+        "lbm_set_compact_offset": ([vp, i64, i64], C.c_int),
+        "lbm_read_vel": ([vp], C.c_int),
+        "lbm_set_bc_planes": ([vp, vp, vp], C.c_int),
+        "lbm_initialize": ([vp], C.c_int),
+        "lbm_step": ([vp, i32], C.c_int),
+        "lbm_step_timed": ([vp, i32, P(C.c_float)], C.c_int),
+        "lbm_step_count": ([vp], i64),
+        "lbm_launch_count": ([vp], i64),
+        "lbm_residual": ([vp, i32, P(dbl)], C.c_int),
+        "lbm_get_geo": ([vp, vp], C.c_int),
+        "lbm_get_index": ([vp, vp], C.c_int),
+        "lbm_get_fields": ([vp, vp, vp, vp, vp, P(i64), P(i64)], C.c_int),
+        "lbm_debug_get_populations": ([vp, vp], C.c_int),
+        "lbm_num_fluid": ([vp], i64),
+        "lbm_device_bytes": ([vp], i64),
+        "lbm_output_save": ([vp, i32], C.c_int),
+        "lbm_run_fixed": ([vp, i32, i32, i32], C.c_int),
+        "lbm_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
+        "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t)], C.c_int),
+        "lbm_step_begin": ([vp, i32], C.c_int),
+        "lbm_step_end": ([vp], C.c_int),
+        "lbm_last_velsum": ([vp, P(dbl)], C.c_int),
+        "lbm_stream": ([vp], vp),
+        "lbm_sync": ([vp], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes, fn.restype = args, res
+    _lib = L
+    return L
+
+
+def case_defaults(case_rule: int) -> CaseDesc:
+    d = CaseDesc()
+    rc = load_library().lbm_case_defaults(case_rule, C.byref(d))
+    if rc:
+        raise LbmError(rc, "unknown case rule")
+    return d
+
+
+class Case:
+    """One simulation.  Methods carry the reference's function names."""
+
+    def __init__(self, desc: CaseDesc):
+        self._L = load_library()
+        self.desc = desc
+        self.dtype = np.dtype(np.float32 if desc.precision == F32 else np.float64)
+        self._h = C.c_void_p()
+        rc = self._L.lbm_create(C.byref(desc), C.byref(self._h))
+        if rc:
+            raise LbmError(rc, self._L.lbm_last_error(None).decode())
+        self.nlattice = None
+        self._keep = []
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc:
+            raise LbmError(rc, self._L.lbm_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def owned_shape(self):
+        d = self.desc
+        return (d.z_end - d.z_begin, d.ny, d.nx)
+
+    def close(self):
+        if self._h:
+            self._L.lbm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference's call sequence
+    def set_flag(self, flag: np.ndarray):
+        """binary voxel field [nz][ny][nx] from memory instead of ./geo.txt"""
+        d = self.desc
+        flag = np.ascontiguousarray(flag, dtype=np.int32)
+        if flag.shape != (d.nz, d.ny, d.nx):
+            raise ValueError(f"flag shape {flag.shape} != {(d.nz, d.ny, d.nx)}")
+        self._ck(self._L.lbm_set_flag(self._h, flag.ctypes.data))
+
+    def geo_pre(self):
+        self._ck(self._L.lbm_geo_pre(self._h))
+
+    def local_stored_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self._L.lbm_local_stored_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_compact_offset(self, offset: int, total: int):
+        self._ck(self._L.lbm_set_compact_offset(self._h, offset, total))
+
+    def index_transform(self) -> int:
+        n = C.c_int64()
+        self._ck(self._L.lbm_index_transform(self._h, C.byref(n)))
+        self.nlattice = n.value
+        return n.value
+
+    def read_vel(self):
+        self._ck(self._L.lbm_read_vel(self._h))
+
+    def set_bc_planes(self, inlet_uy: np.ndarray, outlet_uy: np.ndarray):
+        a = np.ascontiguousarray(inlet_uy, dtype=np.float32)
+        b = np.ascontiguousarray(outlet_uy, dtype=np.float32)
+        n = self.desc.nx * self.desc.nz
+        if a.size != n or b.size != n:
+            raise ValueError("BC planes must hold nx*nz floats")
+        self._ck(self._L.lbm_set_bc_planes(self._h, a.ctypes.data, b.ctypes.data))
+
+    def initialize(self):
+        self._ck(self._L.lbm_initialize(self._h))
+
+    def step(self, n: int = 1):
+        """n iterations of update + boundary_stream + swap"""
+        self._ck(self._L.lbm_step(self._h, int(n)))
+
+    update = step
+
+    def step_timed(self, n: int) -> float:
+        ms = C.c_float()
+        self._ck(self._L.lbm_step_timed(self._h, int(n), C.byref(ms)))
+        return ms.value
+
+    def step_begin(self, flags: int = 0):
+        self._ck(self._L.lbm_step_begin(self._h, flags))
+
+    def step_end(self):
+        self._ck(self._L.lbm_step_end(self._h))
+
+    def last_velsum(self) -> float:
+        v = C.c_double()
+        self._ck(self._L.lbm_last_velsum(self._h, C.byref(v)))
+        return v.value
+
+    def halo_buffers(self, side: int):
+        s, r, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        self._ck(self._L.lbm_halo_buffers(self._h, side, C.byref(s), C.byref(r), C.byref(n)))
+        return s.value, r.value, n.value
+
+    def residual(self, kind: int = RES_VELSUM) -> float:
+        v = C.c_double()
+        self._ck(self._L.lbm_residual(self._h, kind, C.byref(v)))
+        return v.value
+
+    def calc_res(self) -> float:
+        return self.residual(RES_U2SUM)
+
+    def get_geo(self) -> np.ndarray:
+        g = np.empty(self.owned_shape, dtype=np.int32)
+        self._ck(self._L.lbm_get_geo(self._h, g.ctypes.data))
+        return g
+
+    def get_index(self) -> np.ndarray:
+        g = np.empty(self.owned_shape, dtype=np.int32)
+        self._ck(self._L.lbm_get_index(self._h, g.ctypes.data))
+        return g
+
+    def get_fields(self, out=None):
+        """(rho, ux, uy, uz) in the reference's compact order (entries of the owned planes)"""
+        n = self.local_stored_count()
+        if out is None:
+            out = [np.empty(n, dtype=self.dtype) for _ in range(4)]
+        first, count = C.c_int64(), C.c_int64()
+        self._ck(self._L.lbm_get_fields(self._h, *[o.ctypes.data for o in out], C.byref(first), C.byref(count)))
+        self.compact_first, self.compact_count = first.value, count.value
+        return out
+
+    def get_populations(self) -> np.ndarray:
+        n = self.local_stored_count()
+        f = np.empty((19, n), dtype=self.dtype)
+        self._ck(self._L.lbm_debug_get_populations(self._h, f.ctypes.data))
+        return f
+
+    def outputSave(self, t: int):
+        self._ck(self._L.lbm_output_save(self._h, int(t)))
+
+    def run_fixed(self, repeat: int, time_save: int, write_files: bool = True):
+        self._ck(self._L.lbm_run_fixed(self._h, repeat, time_save, int(write_files)))
+
+    def run_converge(self, max_it=10000, tol=1e-6, stag_max=50, time_save=500, write_files=True):
+        its, res = C.c_int32(), C.c_double()
+        self._ck(self._L.lbm_run_converge(self._h, max_it, tol, stag_max, time_save, int(write_files),
+                                          C.byref(its), C.byref(res)))
+        return its.value, res.value
+
+    def sync(self):
+        self._ck(self._L.lbm_sync(self._h))
+
+    @property
+    def num_fluid(self) -> int:
+        return self._L.lbm_num_fluid(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return self._L.lbm_launch_count(self._h)
+
+    @property
+    def step_count(self) -> int:
+        return self._L.lbm_step_count(self._h)
+
+    @property
+    def device_bytes(self) -> int:
+        return self._L.lbm_device_bytes(self._h)
+
+    @property
+    def stream(self) -> int:
+        return self._L.lbm_stream(self._h)
+
+
+def make_case(case_rule: int, *, n=None, dims=None, precision=F32, math_mode=MATH_FAST, storage=STORE_DENSE_AB,
+              tau=None, device=0, z_range=None, **paths) -> Case:
+    """Reference defaults for `case_rule`, optionally resized (cube `n` or `dims=(nx,ny,nz)`)."""
+    d = case_defaults(case_rule)
+    if n is not None:
+        dims = (n, n, n)
+    if dims is not None:
+        d.nx, d.ny, d.nz = dims
+        d.z_begin, d.z_end = 0, d.nz
+    if z_range is not None:
+        d.z_begin, d.z_end = z_range
+    d.precision, d.math, d.storage, d.device = precision, math_mode, storage, device
+    if tau is not None:
+        d.tau = tau
+    for k, v in paths.items():
+        setattr(d, k, os.fsencode(str(v)))
+    return Case(d)

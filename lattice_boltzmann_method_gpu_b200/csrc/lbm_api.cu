@@ -1,0 +1,981 @@
+// Host side of liblbm_b200.so: the solver object behind the opaque handle, the
+// C ABI of include/lbm_b200.h, the geo.txt / bc.txt readers and the
+// byte-compatible VTK / CONVERGENCE.log writers.
+//
+// There is deliberately no CPU fallback: without a CUDA device lbm_create
+// fails with LBM_ERR_NO_DEVICE.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <new>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "lbm_internal.h"
+
+namespace lbm {
+
+static thread_local std::string g_create_error;
+
+static std::string fmt(const char *f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+struct SolverBase {
+    virtual ~SolverBase() {}
+    std::string err;
+    lbm_case_desc d{};
+    virtual int set_flag(const int32_t *flag) = 0;
+    virtual int geo_pre() = 0;
+    virtual int index_transform(int64_t *nlat) = 0;
+    virtual int local_stored_count(int64_t *n) = 0;
+    virtual int set_compact_offset(int64_t off, int64_t total) = 0;
+    virtual int read_vel() = 0;
+    virtual int set_bc_planes(const float *in, const float *out) = 0;
+    virtual int initialize() = 0;
+    virtual int step(int n, float *ms) = 0;
+    virtual int step_begin(int flags) = 0;
+    virtual int step_end() = 0;
+    virtual int last_velsum(double *v) = 0;
+    virtual int residual(int kind, double *v) = 0;
+    virtual int get_geo(int32_t *g) = 0;
+    virtual int get_index(int32_t *g) = 0;
+    virtual int get_fields(void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count) = 0;
+    virtual int get_populations(void *f) = 0;
+    virtual int output_save(int t) = 0;
+    virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
+    virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
+                             double *res) = 0;
+    virtual int halo_buffers(int side, void **send, void **recv, size_t *bytes) = 0;
+    virtual int sync() = 0;
+    virtual void *stream_ptr() = 0;
+    int64_t steps = 0, launches = 0, nfluid = 0, dev_bytes = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            err = fmt("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return e_ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA;                 \
+        }                                                                                          \
+    } while (0)
+#define FAIL(code, ...)         \
+    do {                        \
+        err = fmt(__VA_ARGS__); \
+        return code;            \
+    } while (0)
+
+template <typename T>
+struct Solver final : SolverBase {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Box ext{}, box{};
+    int own_z0 = 0, own_z1 = 0;
+    bool lo_halo = false, hi_halo = false;
+    int fluid_label = 4;
+    GeoRules rules{};
+    BcEntry bc[LBM_MAX_BC]{};
+    // stage flags
+    bool have_flag = false, have_geo = false, have_index = false, have_init = false, have_planes = false;
+    bool have_moments = false, in_step = false;
+    int step_flags = 0;
+    // host
+    std::vector<int32_t> h_flag;  // global Cartesian, optional
+    std::vector<float> h_in, h_out;
+    // device
+    uint8_t *d_flag = nullptr;
+    int32_t *d_label_ext = nullptr, *d_label = nullptr, *d_index = nullptr, *d_scratch = nullptr;
+    uint32_t *d_node = nullptr;
+    uint8_t *d_seg = nullptr;
+    int8_t *d_label8 = nullptr;
+    T *d_fa = nullptr, *d_fb = nullptr, *d_cur = nullptr, *d_nxt = nullptr;
+    T *d_rho = nullptr, *d_ux = nullptr, *d_uy = nullptr, *d_uz = nullptr;
+    T *d_plane_in = nullptr, *d_plane_out = nullptr;
+    T *d_send[2] = {nullptr, nullptr}, *d_recv[2] = {nullptr, nullptr};
+    double *d_acc = nullptr;      // [ACC_SLOTS] reduction slots
+    long long *d_cnt = nullptr;   // small device counters
+    static constexpr int ACC_SLOTS = 64;
+    long long qstride = 0;
+    int64_t stored_own = 0, compact_first = 0, compact_total = -1;
+    bool offset_set = false;
+    size_t scratch_ints = 0;
+    double last_S = 0.0;
+
+    ~Solver() override {
+        cudaSetDevice(d.device);
+        auto fr = [](void *p) {
+            if (p) cudaFree(p);
+        };
+        fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
+        fr(d_fa), fr(d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
+        fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+    }
+
+    // the LDC rule stores every node of the box (ldc.cu:54); the others store geo != 0
+    int store_all() const { return d.case_rule == LBM_CASE_LDC ? 1 : 0; }
+
+    template <typename U>
+    int dalloc(U **p, size_t n) {
+        CK(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(U)));
+        dev_bytes += (int64_t)(n * sizeof(U));
+        return 0;
+    }
+
+    int setup() {
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        fluid_label = d.case_rule == LBM_CASE_LDC ? 3 : 4;
+        own_z0 = d.z_begin, own_z1 = d.z_end;
+        lo_halo = own_z0 > 0, hi_halo = own_z1 < d.nz;
+        const int px = ((d.nx + 31) / 32) * 32;
+        box.nx = d.nx, box.ny = d.ny, box.nz = d.nz, box.px = px, box.plane = (long long)px * d.ny;
+        box.z0 = own_z0 - (lo_halo ? 1 : 0), box.z1 = own_z1 + (hi_halo ? 1 : 0);
+        ext = box;
+        ext.z0 = std::max(0, own_z0 - 3), ext.z1 = std::min(d.nz, own_z1 + 3);
+        if (box.cells() * 19 >= (1LL << 40)) FAIL(LBM_ERR_ARG, "box too large");
+        rules.case_rule = d.case_rule;
+        rules.n_open = d.n_openings;
+        for (int i = 0; i < d.n_openings; i++) rules.open[i] = d.openings[i];
+        rules.mark_sources = d.case_rule == LBM_CASE_LDC ? 0u
+                             : d.case_rule == LBM_CASE_POISEUILLE ? ((1u << 1) | (1u << 2) | (1u << 3))
+                                                                  : (1u << 1);
+        for (auto &e : bc) e = BcEntry{LBM_BC_NONE, 0, 0, 0, 0, 0, 0.0, 0.0};
+        for (int i = 0; i < d.n_bc; i++) {
+            const lbm_bc_desc &s = d.bc[i];
+            if (s.label < 1 || s.label >= LBM_MAX_BC || s.label == fluid_label)
+                FAIL(LBM_ERR_ARG, "bc[%d]: label %d not a boundary label", i, s.label);
+            if (s.normal_axis < 0 || s.normal_axis > 2 || s.vel_axis < 0 || s.vel_axis > 2 ||
+                (s.normal_sign != 1 && s.normal_sign != -1))
+                FAIL(LBM_ERR_ARG, "bc[%d]: bad axis/sign", i);
+            bc[s.label] = BcEntry{s.kind, s.normal_axis, s.normal_sign, s.vel_axis, s.source, s.pulsatile, s.value,
+                                  s.init_value};
+        }
+        if (dalloc(&d_acc, ACC_SLOTS) || dalloc(&d_cnt, 8)) return LBM_ERR_NOMEM;
+        return 0;
+    }
+
+    // ------------------------------------------------------------ geometry
+    int set_flag(const int32_t *flag) override {
+        if (!flag) FAIL(LBM_ERR_ARG, "null flag");
+        h_flag.assign(flag, flag + (size_t)d.nx * d.ny * d.nz);
+        have_flag = true;
+        return 0;
+    }
+
+    int load_flag_file() {
+        FILE *f = fopen(d.geo_path, "r");
+        if (!f) FAIL(LBM_ERR_IO, "cannot open geometry file '%s'", d.geo_path);
+        h_flag.assign((size_t)d.nx * d.ny * d.nz, 0);
+        long cnt = 0;
+        int tmp;
+        // bif.cu:50-61 (x fastest) or cor.cu:45-56 (y fastest)
+        for (int z = 0; z < d.nz; z++) {
+            const int n1 = d.geo_yfast ? d.nx : d.ny, n2 = d.geo_yfast ? d.ny : d.nx;
+            for (int a = 0; a < n1; a++)
+                for (int b = 0; b < n2; b++) {
+                    if (fscanf(f, "%d ", &tmp) != 1) tmp = 0;
+                    else cnt++;
+                    int x = d.geo_yfast ? a : b, y = d.geo_yfast ? b : a;
+                    h_flag[(size_t)x + (size_t)d.nx * ((size_t)y + (size_t)d.ny * z)] = tmp;
+                }
+        }
+        fclose(f);
+        if (cnt != (long)d.nx * d.ny * d.nz)
+            FAIL(LBM_ERR_IO, "geometry file '%s' holds %ld tokens, expected %ld", d.geo_path, cnt,
+                 (long)d.nx * d.ny * d.nz);
+        have_flag = true;
+        return 0;
+    }
+
+    int geo_pre() override {
+        CK(cudaSetDevice(d.device));
+        const bool needs_file = d.case_rule == LBM_CASE_GEO_Y_INOUT || d.case_rule == LBM_CASE_GEO_OPENINGS;
+        if (needs_file && !have_flag) {
+            int r = load_flag_file();
+            if (r) return r;
+        }
+        if (!d_flag && dalloc(&d_flag, (size_t)ext.cells())) return LBM_ERR_NOMEM;
+        if (!d_label_ext && dalloc(&d_label_ext, (size_t)ext.cells())) return LBM_ERR_NOMEM;
+        if (needs_file) {
+            // ext slab of the binary field, padded pitch, one byte per voxel
+            std::vector<uint8_t> tmp((size_t)ext.cells(), 0);
+            for (int z = ext.z0; z < ext.z1; z++)
+                for (int y = 0; y < d.ny; y++) {
+                    const int32_t *srow = &h_flag[(size_t)d.nx * ((size_t)y + (size_t)d.ny * z)];
+                    uint8_t *drow = &tmp[(size_t)ext.px * ((size_t)y + (size_t)d.ny * (z - ext.z0))];
+                    for (int x = 0; x < d.nx; x++) drow[x] = (uint8_t)srow[x];
+                }
+            CK(cudaMemcpyAsync(d_flag, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        } else if (d.case_rule == LBM_CASE_POISEUILLE) {
+            CK(launch_make_flag_pos(d_flag, ext, st));
+            launches++;
+        } else {
+            CK(cudaMemsetAsync(d_flag, 0, (size_t)ext.cells(), st));
+        }
+        CK(launch_labels(d_flag, d_label_ext, ext, rules, st));
+        CK(launch_mark(d_label_ext, ext, rules, st));
+        launches += 2;
+        if (!d_label && dalloc(&d_label, (size_t)box.cells())) return LBM_ERR_NOMEM;
+        CK(cudaMemcpyAsync(d_label, d_label_ext + (long long)(box.z0 - ext.z0) * ext.plane,
+                           (size_t)box.cells() * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        // owned stored-node count (needed by multi-slab callers before index_transform)
+        CK(launch_count_stored(d_label + (long long)(own_z0 - box.z0) * box.plane,
+                               (long long)(own_z1 - own_z0) * box.plane, box.px, box.nx, store_all(), d_cnt, st));
+        launches++;
+        long long c = 0;
+        CK(cudaMemcpyAsync(&c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        stored_own = c;
+        have_geo = true, have_index = false, have_init = false;
+        return 0;
+    }
+
+    int local_stored_count(int64_t *n) override {
+        if (!have_geo) FAIL(LBM_ERR_STATE, "geo_pre has not run");
+        *n = stored_own;
+        return 0;
+    }
+    int set_compact_offset(int64_t off, int64_t total) override {
+        compact_first = off, compact_total = total, offset_set = true;
+        return 0;
+    }
+
+    int index_transform(int64_t *nlat) override {
+        if (!have_geo) FAIL(LBM_ERR_STATE, "index_transform before geo_pre");
+        CK(cudaSetDevice(d.device));
+        if ((lo_halo || hi_halo) && !offset_set)
+            FAIL(LBM_ERR_STATE, "slab handle: call lbm_set_compact_offset before lbm_index_transform");
+        if (!offset_set) compact_first = 0, compact_total = stored_own;
+        if (!d_index && dalloc(&d_index, (size_t)box.cells())) return LBM_ERR_NOMEM;
+        long long n_lo = 0;
+        if (lo_halo) {
+            CK(launch_count_stored(d_label, box.plane, box.px, box.nx, store_all(), d_cnt + 1, st));
+            launches++;
+            CK(cudaMemcpyAsync(&n_lo, d_cnt + 1, sizeof n_lo, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        scratch_ints = compact_scratch_ints(box.cells());
+        if (!d_scratch && dalloc(&d_scratch, scratch_ints)) return LBM_ERR_NOMEM;
+        CK(launch_compact(d_label, d_index, box.cells(), box.px, box.nx, store_all(), (long long)compact_first - n_lo,
+                          d_scratch, scratch_ints, d_cnt + 2, st));
+        launches += 3;
+        // node words, segment classes, int8 labels
+        if (!d_node) {
+            if (dalloc(&d_node, (size_t)box.cells()) || dalloc(&d_seg, (size_t)(box.cells() / 32 + 1)) ||
+                dalloc(&d_label8, (size_t)box.cells()))
+                return LBM_ERR_NOMEM;
+        }
+        CK(launch_node_words(d_label, d_node, d_seg, d_label8, box, own_z0, own_z1, fluid_label, d_cnt + 3, st));
+        launches++;
+        long long nf = 0;
+        CK(cudaMemcpyAsync(&nf, d_cnt + 3, sizeof nf, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nfluid = nf;
+        have_index = true;
+        if (nlat) *nlat = compact_total;
+        return 0;
+    }
+
+    // label of global cell (x,y,z) for host-side masking; 0 when outside the state box
+    int fetch_label_rows(int y, std::vector<int32_t> &rows) {
+        // rows[z_local*px + x] for all planes of the state box
+        const int nzl = box.z1 - box.z0;
+        rows.assign((size_t)nzl * box.px, 0);
+        CK(cudaMemcpy2DAsync(rows.data(), (size_t)box.px * sizeof(int32_t), d_label + (long long)y * box.px,
+                             (size_t)box.plane * sizeof(int32_t), (size_t)box.px * sizeof(int32_t), nzl,
+                             cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+
+    int upload_planes() {
+        const size_t n = (size_t)d.nx * d.nz;
+        if (!d_plane_in && (dalloc(&d_plane_in, n) || dalloc(&d_plane_out, n))) return LBM_ERR_NOMEM;
+        std::vector<T> a(n), b(n);
+        for (size_t i = 0; i < n; i++) a[i] = (T)h_in[i], b[i] = (T)h_out[i];
+        CK(cudaMemcpyAsync(d_plane_in, a.data(), n * sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_plane_out, b.data(), n * sizeof(T), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        have_planes = true;
+        return 0;
+    }
+
+    // read_vel(): bif.cu:255-327.  raw planes are masked by the labels at y=1 / y=NY-2.
+    int mask_and_store_planes(const float *in, const float *out) {
+        if (!have_geo) FAIL(LBM_ERR_STATE, "read_vel before geo_pre");
+        std::vector<int32_t> r1, r2;
+        int r = fetch_label_rows(1, r1);
+        if (r) return r;
+        r = fetch_label_rows(d.ny - 2, r2);
+        if (r) return r;
+        const size_t n = (size_t)d.nx * d.nz;
+        h_in.assign(n, 0.f), h_out.assign(n, 0.f);
+        for (int z = box.z0; z < box.z1; z++)
+            for (int x = 0; x < d.nx; x++) {
+                size_t i = (size_t)x + (size_t)z * d.nx, j = (size_t)(z - box.z0) * box.px + x;
+                h_in[i] = r1[j] == 2 ? in[i] : 0.f;
+                h_out[i] = r2[j] == 3 ? out[i] : 0.f;
+            }
+        return upload_planes();
+    }
+    int read_vel() override {
+        FILE *f = fopen(d.bc_path, "r");
+        if (!f) FAIL(LBM_ERR_IO, "cannot open boundary file '%s'", d.bc_path);
+        const size_t n = (size_t)d.nx * d.nz;
+        std::vector<float> a(n, 0.f), b(n, 0.f);
+        float tmp;
+        for (size_t i = 0; i < n; i++) a[i] = fscanf(f, "%f ", &tmp) == 1 ? tmp : 0.f;
+        for (size_t i = 0; i < n; i++) b[i] = fscanf(f, "%f ", &tmp) == 1 ? tmp : 0.f;
+        fclose(f);
+        return mask_and_store_planes(a.data(), b.data());
+    }
+    int set_bc_planes(const float *in, const float *out) override {
+        if (!in || !out) FAIL(LBM_ERR_ARG, "null plane");
+        return mask_and_store_planes(in, out);
+    }
+
+    // ------------------------------------------------------------ state
+    int initialize() override {
+        if (!have_index) FAIL(LBM_ERR_STATE, "initialize before index_transform");
+        CK(cudaSetDevice(d.device));
+        if (d.storage != LBM_STORE_DENSE_AB) FAIL(LBM_ERR_ARG, "storage %d not available in this build", d.storage);
+        if (d.case_rule == LBM_CASE_GEO_Y_INOUT && !have_planes) {
+            h_in.assign((size_t)d.nx * d.nz, 0.f), h_out = h_in;
+            int r = upload_planes();
+            if (r) return r;
+        }
+        if (!d_plane_in) {
+            h_in.assign((size_t)d.nx * d.nz, 0.f), h_out = h_in;
+            int r = upload_planes();
+            if (r) return r;
+        }
+        const long long cells = box.cells();
+        qstride = cells + 64;  // de-phase the 19 streams a little; keeps 256-B alignment
+        if (!d_fa) {
+            if (dalloc(&d_fa, (size_t)qstride * Q) || dalloc(&d_fb, (size_t)qstride * Q)) return LBM_ERR_NOMEM;
+            if (dalloc(&d_rho, (size_t)cells) || dalloc(&d_ux, (size_t)cells) || dalloc(&d_uy, (size_t)cells) ||
+                dalloc(&d_uz, (size_t)cells))
+                return LBM_ERR_NOMEM;
+            for (int s = 0; s < 2; s++)
+                if (dalloc(&d_send[s], (size_t)box.plane * 5) || dalloc(&d_recv[s], (size_t)box.plane * 5))
+                    return LBM_ERR_NOMEM;
+        }
+        InitParams<T> ip{};
+        ip.fa = d_fa, ip.fb = d_fb, ip.qstride = qstride, ip.label = d_label;
+        ip.rho = d_rho, ip.ux = d_ux, ip.uy = d_uy, ip.uz = d_uz;
+        ip.box = box, ip.case_rule = d.case_rule, ip.u_max = (T)d.u_max;
+        for (int i = 0; i < LBM_MAX_BC; i++) ip.bc[i] = bc[i];
+        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out;
+        CK(launch_init<T>(ip, st));
+        launches++;
+        CK(cudaStreamSynchronize(st));
+        d_cur = d_fa, d_nxt = d_fb;
+        steps = 0;
+        have_init = true, have_moments = false, in_step = false;
+        return 0;
+    }
+
+    StepParams<T> make_params(long long c0, long long c1, double *acc) {
+        StepParams<T> p{};
+        p.src = d_cur, p.dst = d_nxt, p.qstride = qstride;
+        p.node = d_node, p.seg = d_seg, p.label8 = d_label8;
+        p.rho = d_rho, p.ux = d_ux, p.uy = d_uy, p.uz = d_uz;
+        p.resid = acc;
+        p.box = box, p.c_begin = c0, p.c_end = c1;
+        p.fluid_label = fluid_label;
+        p.tau = (T)d.tau;
+        p.inv_tau = T(1.0) / p.tau;
+        p.om1 = T(1.0) - T(1.0) / p.tau;
+        double sc = 1.0;
+        if (d.pulse_amp != 0.0) sc = 1.0 + d.pulse_amp * std::sin(2.0 * M_PI * (double)steps / d.pulse_period);
+        p.pulse_scale = (T)sc;
+        for (int i = 0; i < LBM_MAX_BC; i++) p.bc[i] = bc[i];
+        p.plane_in = d_plane_in, p.plane_out = d_plane_out;
+        p.parity = (int)(steps & 1);
+        return p;
+    }
+    int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc) {
+        if (c1 <= c0) return 0;
+        StepParams<T> p = make_params(c0, c1, acc);
+        if (d.math == LBM_MATH_STRICT) CK(launch_step_dense_strict<T>(p, moments, resid, d.storage, st));
+        else CK(launch_step_dense_fast<T>(p, moments, resid, d.storage, st));
+        launches++;
+        return 0;
+    }
+    long long plane_c(int z_global) const { return (long long)(z_global - box.z0) * box.plane; }
+
+    // single-domain step loop
+    int step(int n, float *ms) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "step before initialize");
+        if (lo_halo || hi_halo) FAIL(LBM_ERR_STATE, "slab handle: use lbm_step_begin / lbm_step_end");
+        if (n < 0) FAIL(LBM_ERR_ARG, "negative step count");
+        CK(cudaSetDevice(d.device));
+        if (ms) CK(cudaEventRecord(ev0, st));
+        for (int i = 0; i < n; i++) {
+            int r = launch_range(plane_c(own_z0), plane_c(own_z1), i == n - 1, false, nullptr);
+            if (r) return r;
+            std::swap(d_cur, d_nxt);
+            steps++;
+        }
+        if (n > 0) have_moments = true;
+        if (ms) {
+            CK(cudaEventRecord(ev1, st));
+            CK(cudaEventSynchronize(ev1));
+            CK(cudaEventElapsedTime(ms, ev0, ev1));
+        } else {
+            CK(cudaStreamSynchronize(st));
+        }
+        return 0;
+    }
+
+    // one step with an optional velsum slot; used by run_converge and the slab protocol
+    int step_begin(int flags) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "step before initialize");
+        if (in_step) FAIL(LBM_ERR_STATE, "lbm_step_begin called twice");
+        CK(cudaSetDevice(d.device));
+        const bool mom = flags & LBM_STEP_MOMENTS, res = flags & LBM_STEP_VELSUM;
+        step_flags = flags;
+        if (res) CK(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
+        int r;
+        const int zt = own_z1 - 1, zb = own_z0;
+        long long i0 = plane_c(own_z0), i1 = plane_c(own_z1);
+        if (hi_halo) {
+            if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, d_acc))) return r;
+            CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
+            launches++;
+            i1 = plane_c(zt);
+        }
+        if (lo_halo && !(hi_halo && zb == zt)) {
+            if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, d_acc))) return r;
+            i0 = plane_c(zb + 1);
+        }
+        if (lo_halo) {
+            CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
+            launches++;
+        }
+        if ((r = launch_range(i0, i1, mom, res, d_acc))) return r;
+        in_step = true;
+        return 0;
+    }
+    int step_end() override {
+        if (!in_step) FAIL(LBM_ERR_STATE, "lbm_step_end without lbm_step_begin");
+        CK(cudaSetDevice(d.device));
+        if (lo_halo) {
+            CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
+            launches++;
+        }
+        if (hi_halo) {
+            CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
+            launches++;
+        }
+        if (step_flags & LBM_STEP_VELSUM) {
+            CK(cudaMemcpyAsync(&last_S, d_acc, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (step_flags & LBM_STEP_MOMENTS) have_moments = true;
+        std::swap(d_cur, d_nxt);
+        steps++;
+        in_step = false;
+        return 0;
+    }
+    int last_velsum(double *v) override {
+        *v = last_S;
+        return 0;
+    }
+    int halo_buffers(int side, void **send, void **recv, size_t *bytes) override {
+        if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
+        if (!have_init) FAIL(LBM_ERR_STATE, "halo_buffers before initialize");
+        const bool present = side == 0 ? lo_halo : hi_halo;
+        if (send) *send = present ? d_send[side] : nullptr;
+        if (recv) *recv = present ? d_recv[side] : nullptr;
+        if (bytes) *bytes = present ? (size_t)box.plane * 5 * sizeof(T) : 0;
+        return 0;
+    }
+
+    int residual(int kind, double *v) override {
+        if (!have_moments) FAIL(LBM_ERR_STATE, "no moments yet: run lbm_step first");
+        CK(cudaSetDevice(d.device));
+        CK(launch_reduce_fields<T>(d_ux, d_uy, d_uz, d_label, box, own_z0, own_z1, kind, fluid_label, d.case_rule,
+                                   d_acc + 1, st));
+        launches++;
+        CK(cudaMemcpyAsync(v, d_acc + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+
+    // ------------------------------------------------------------ readback
+    int get_box_i32(const int32_t *dev, int32_t *out) {
+        CK(cudaSetDevice(d.device));
+        const int nzo = own_z1 - own_z0;
+        CK(cudaMemcpy2DAsync(out, (size_t)d.nx * sizeof(int32_t), dev + plane_c(own_z0), (size_t)box.px * sizeof(int32_t),
+                             (size_t)d.nx * sizeof(int32_t), (size_t)d.ny * nzo, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    int get_geo(int32_t *g) override {
+        if (!have_geo) FAIL(LBM_ERR_STATE, "get_geo before geo_pre");
+        return get_box_i32(d_label, g);
+    }
+    int get_index(int32_t *g) override {
+        if (!have_index) FAIL(LBM_ERR_STATE, "get_index before index_transform");
+        return get_box_i32(d_index, g);
+    }
+    int get_fields(void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "get_fields before initialize");
+        CK(cudaSetDevice(d.device));
+        const size_t n = (size_t)stored_own;
+        T *tmp = nullptr;
+        CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * 4 * sizeof(T)));
+        cudaError_t e = cudaMemsetAsync(tmp, 0, n * 4 * sizeof(T), st);
+        if (e == cudaSuccess)
+            e = launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, own_z0, own_z1, fluid_label,
+                                        compact_first, tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, st);
+        launches++;
+        void *outs[4] = {rho, ux, uy, uz};
+        for (int k = 0; k < 4 && e == cudaSuccess; k++)
+            if (outs[k]) e = cudaMemcpyAsync(outs[k], tmp + k * n, n * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        CK(e);
+        if (first) *first = compact_first;
+        if (count) *count = stored_own;
+        return 0;
+    }
+    int get_populations(void *f) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "get_populations before initialize");
+        CK(cudaSetDevice(d.device));
+        const size_t n = (size_t)stored_own;
+        T *tmp = nullptr;
+        CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * Q * sizeof(T)));
+        cudaError_t e = launch_gather_pops<T>(d_cur, qstride, d_index, box, own_z0, own_z1, compact_first, (long long)n,
+                                              tmp, st);
+        launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f, tmp, n * Q * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        CK(e);
+        return 0;
+    }
+
+    // ------------------------------------------------------------ writers
+    // Host copies in Cartesian order for the writers (single-domain handles).
+    std::vector<int32_t> w_index;
+    std::vector<T> w_rho, w_ux, w_uy, w_uz;
+    int fetch_for_output() {
+        if (lo_halo || hi_halo) FAIL(LBM_ERR_STATE, "writers need a single-domain handle");
+        if (w_index.empty()) {
+            w_index.resize((size_t)d.nx * d.ny * d.nz);
+            int r = get_index(w_index.data());
+            if (r) return r;
+        }
+        const size_t n = (size_t)stored_own;
+        w_rho.resize(n), w_ux.resize(n), w_uy.resize(n), w_uz.resize(n);
+        return get_fields(w_rho.data(), w_ux.data(), w_uy.data(), w_uz.data(), nullptr, nullptr);
+    }
+
+    // outputSave: ldc.cu:582-610, pos:903-938, bif:1095-1156, cor:948-1011.
+    // Same loops, same `ofstream <<` formatting of float values.
+    int output_save(int t) override {
+        int r = fetch_for_output();
+        if (r) return r;
+        const int NX = d.nx, NY = d.ny, NZ = d.nz;
+        const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
+        const float C_pre = C_rho * C_U * C_U;
+        std::string path = std::string(d.out_dir) + "/" + d.out_name + "_" + std::to_string(t) + ".vtk";
+        std::ofstream ofs(path);
+        if (!ofs) FAIL(LBM_ERR_IO, "cannot write '%s'", path.c_str());
+        using std::endl;
+        ofs << "# vtk DataFile Version 2.0" << endl;
+        ofs << "<-- LBM flow with UIV acceleration, http://www.bg.ic.ac.uk/research/m.tang/ulis/ -->" << endl;
+        ofs << "ASCII" << endl;
+        ofs << "DATASET STRUCTURED_POINTS" << endl;
+        const bool ldc = d.case_rule == LBM_CASE_LDC;
+        const int x0 = ldc ? 2 : 1, x1 = ldc ? NX - 2 : NX - 1, y0 = 2, y1 = NY - 2, z0 = ldc ? 2 : 1,
+                  z1 = ldc ? NZ - 2 : NZ - 1;
+        ofs << "DIMENSIONS " << (x1 - x0) << ' ' << (y1 - y0) << ' ' << (z1 - z0) << endl;
+        ofs << "SPACING " << CH << ' ' << CH << ' ' << CH << endl;
+        if (ldc) ofs << "ORIGIN " << std::round(NX / 2 - 1) * CH << ' ' << std::round(NY / 2 - 1) * CH << ' ' << .0 << endl;
+        else ofs << "ORIGIN " << std::round(NX / 2) * CH << ' ' << std::round(NY / 2) * CH << ' ' << .0 << endl;
+        ofs << "POINT_DATA  " << (x1 - x0) * (y1 - y0) * (z1 - z0) << endl;
+        auto idx_of = [&](int x, int y, int z) { return w_index[(size_t)x + (size_t)NX * ((size_t)y + (size_t)NY * z)]; };
+        if (d.case_rule == LBM_CASE_GEO_OPENINGS) {
+            ofs << "SCALARS DENSITY float" << endl << "LOOKUP_TABLE default" << endl;
+            for (int z = z0; z < z1; z++)
+                for (int y = y0; y < y1; y++)
+                    for (int x = x0; x < x1; x++) {
+                        int i = idx_of(x, y, z);
+                        if (i >= 0) ofs << (float)w_rho[i] * C_rho << ' ';
+                        else ofs << 0.0f << ' ';
+                    }
+            ofs << endl;
+            ofs << "SCALARS PRESSURE float" << endl << "LOOKUP_TABLE default" << endl;
+            for (int z = z0; z < z1; z++)
+                for (int y = y0; y < y1; y++)
+                    for (int x = x0; x < x1; x++) {
+                        int i = idx_of(x, y, z);
+                        if (i >= 0) ofs << (float)w_rho[i] * C_pre / 3.0 << ' ';
+                        else ofs << 0.0f << ' ';
+                    }
+            ofs << endl;
+        }
+        ofs << "VECTORS VELOCITY float" << endl;
+        for (int z = z0; z < z1; z++)
+            for (int y = y0; y < y1; y++)
+                for (int x = x0; x < x1; x++) {
+                    int i = idx_of(x, y, z);
+                    if (i >= 0) {
+                        ofs << (float)w_ux[i] * C_U << ' ';
+                        ofs << (float)w_uy[i] * C_U << ' ';
+                        ofs << (float)w_uz[i] * C_U << ' ';
+                    } else {
+                        ofs << 0 << ' ' << 0 << ' ' << 0 << ' ';
+                    }
+                }
+        ofs.close();
+        return 0;
+    }
+
+    // calc_res(): bif.cu:1158-1175 on the host copy, long double like the reference
+    long double host_u2sum() {
+        long double sum = 0.0L;
+        if (w_index.empty() || w_ux.empty()) return sum;
+        std::vector<int32_t> geo((size_t)d.nx * d.ny * d.nz);
+        if (get_geo(geo.data())) return sum;
+        for (int z = 1; z < d.nz - 1; z++)
+            for (int y = 2; y < d.ny - 2; y++)
+                for (int x = 1; x < d.nx - 1; x++) {
+                    size_t c = (size_t)x + (size_t)d.nx * ((size_t)y + (size_t)d.ny * z);
+                    int g = geo[c];
+                    bool ok = d.case_rule == LBM_CASE_GEO_OPENINGS ? g == 4 : g >= 4;
+                    if (!ok) continue;
+                    int i = w_index[c];
+                    float v = (float)w_ux[i] * (float)w_ux[i] + (float)w_uy[i] * (float)w_uy[i] +
+                              (float)w_uz[i] * (float)w_uz[i];
+                    sum += v;
+                }
+        return sum;
+    }
+
+    // bif.cu:1246-1274 / cor.cu:1100-1132
+    int run_fixed(int repeat, int time_save, int write_files) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "run before initialize");
+        if (time_save <= 0) FAIL(LBM_ERR_ARG, "time_save must be positive");
+        std::ofstream logfile;
+        if (write_files) logfile.open(std::string(d.out_dir) + "/CONVERGENCE.log");
+        auto t0 = std::chrono::steady_clock::now();
+        float residual = 0.f;
+        int done = 0;  // iterations executed so far (loop index i runs 0..repeat inclusive)
+        long double sum1 = 0.0L;
+        while (done <= repeat) {
+            // next save happens at loop index i with i % time_save == 0
+            int i_save = ((done + time_save - 1) / time_save) * time_save;
+            int upto = std::min(i_save, repeat);
+            int r = step(upto - done + 1, nullptr);
+            if (r) return r;
+            done = upto + 1;
+            if (upto % time_save == 0) {
+                sum1 = host_u2sum();  // fields of the previous save (0 at first)
+                r = fetch_for_output();
+                if (r) return r;
+                long double sum2 = host_u2sum();
+                residual = (float)(fabsl(sum1 - sum2) / sum2);
+                float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (write_files) {
+                    logfile << residual << std::endl;
+                    std::cout << "ITERATION # " << upto << ", collapse time: " << milli << " ms, residual:" << residual
+                              << std::endl;
+                    r = output_save(upto);
+                    if (r) return r;
+                }
+            }
+        }
+        float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (write_files) {
+            std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << std::endl;
+            logfile << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << " ERROR IS"
+                    << residual << std::endl;
+        }
+        return 0;
+    }
+
+    // ldc.cu:653-685 / pos.cu:986-1019: residual every step, cumulative tol_count.
+    // Steps run in batches that end on save iterations; S_k of each step lands in
+    // its own device slot, so the host applies the reference's stopping rule
+    // exactly without a sync per step.  Once the tolerance was hit for the
+    // first time the batch size drops to 1, so the loop stops on the same k.
+    int run_converge(int max_it, double tol_d, int stag_max, int time_save, int write_files, int *its,
+                     double *res) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "run before initialize");
+        if (lo_halo || hi_halo) FAIL(LBM_ERR_STATE, "run_converge needs a single-domain handle");
+        if (time_save <= 0) FAIL(LBM_ERR_ARG, "time_save must be positive");
+        CK(cudaSetDevice(d.device));
+        std::ofstream logfile;
+        if (write_files) logfile.open(std::string(d.out_dir) + "/CONVERGENCE.log");
+        auto t0 = std::chrono::steady_clock::now();
+        const float tol = (float)tol_d;
+        float residual = 0.f, sum_current = 0.f;
+        int k = 0, tol_count = 0;
+        const int max_batch = std::max(1, std::min({ACC_SLOTS - 2, stag_max / 2, 32}));
+        std::vector<double> S(ACC_SLOTS);
+        while (k <= max_it && tol_count <= stag_max) {
+            int nb = tol_count > 0 ? 1 : max_batch;
+            nb = std::min(nb, max_it - k + 1);
+            // the batch covers iterations k .. k+nb-1; a save iteration inside must be the last one
+            for (int j = 0; j < nb; j++)
+                if ((k + j) % time_save == 0) {
+                    nb = j + 1;
+                    break;
+                }
+            CK(cudaMemsetAsync(d_acc + 2, 0, sizeof(double) * nb, st));
+            for (int j = 0; j < nb; j++) {
+                int r = launch_range(plane_c(own_z0), plane_c(own_z1), true, true, d_acc + 2 + j);
+                if (r) return r;
+                std::swap(d_cur, d_nxt);
+                steps++;
+            }
+            have_moments = true;
+            CK(cudaMemcpyAsync(S.data(), d_acc + 2, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int j = 0; j < nb; j++) {
+                float sum_next = (float)S[j];
+                residual = std::fabs(sum_next - sum_current) / sum_next;
+                if (k % time_save == 0 && write_files) {
+                    float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    std::cout << "ITERATION # " << k << ", collapse time: " << milli << " ms, residual:" << residual
+                              << std::endl;
+                    logfile << residual << std::endl;
+                    int r = output_save(k);
+                    if (r) return r;
+                }
+                k++;
+                sum_current = sum_next;
+                if (residual <= tol) tol_count++;
+                if (!(k <= max_it && tol_count <= stag_max)) break;
+            }
+        }
+        float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (write_files) {
+            int r = output_save(k);
+            if (r) return r;
+            std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << std::endl;
+            std::cout << "Residual is " << residual << std::endl;
+            logfile << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << " ERROR IS"
+                    << residual << std::endl;
+        }
+        if (its) *its = k;
+        if (res) *res = residual;
+        return 0;
+    }
+
+    int sync() override {
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    void *stream_ptr() override { return (void *)st; }
+};
+
+}  // namespace lbm
+
+// ============================================================================
+// C ABI
+// ============================================================================
+using lbm::SolverBase;
+struct lbm_solver_s {
+    SolverBase *s;
+};
+
+static void set_bc(lbm_case_desc *d, int label, int kind, int naxis, int nsign, int vaxis, int source, double value,
+                   double init_value) {
+    lbm_bc_desc &b = d->bc[d->n_bc++];
+    b.label = label, b.kind = kind, b.normal_axis = naxis, b.normal_sign = nsign, b.vel_axis = vaxis;
+    b.source = source, b.pulsatile = 0, b.reserved = 0, b.value = value, b.init_value = init_value;
+}
+static void set_open(lbm_case_desc *d, int axis, int coord, int lo_a, int hi_a, int lo_b, int hi_b, int reps) {
+    lbm_opening_rule &o = d->openings[d->n_openings++];
+    o.axis = axis, o.coord = coord, o.lo_a = lo_a, o.hi_a = hi_a, o.lo_b = lo_b, o.hi_b = hi_b, o.reps = reps;
+    o.reserved = 0;
+}
+
+extern "C" {
+
+int lbm_case_defaults(int32_t rule, lbm_case_desc *d) {
+    if (!d) return LBM_ERR_ARG;
+    memset(d, 0, sizeof *d);
+    d->struct_size = (int32_t)sizeof *d;
+    d->case_rule = rule;
+    d->precision = LBM_F32;  // the reference's precision (thesis section 4.4)
+    d->storage = LBM_STORE_DENSE_AB;
+    d->math = LBM_MATH_FAST;
+    snprintf(d->geo_path, sizeof d->geo_path, "./geo.txt");
+    snprintf(d->bc_path, sizeof d->bc_path, "./bc.txt");
+    snprintf(d->out_dir, sizeof d->out_dir, "./out");
+    // constants are the reference's float literals, widened
+    switch (rule) {
+    case LBM_CASE_LDC: {  // ldc.cu:48-55
+        d->nx = d->ny = d->nz = 64;
+        const float C_U = 2.4705f;
+        d->tau = 0.55f, d->C_U = C_U, d->C_rho = 1060.f, d->CH = 0.0000655737f;
+        d->u_max = 0.15f / C_U;
+        set_bc(d, 2, LBM_BC_V, 1, -1, 2, LBM_SRC_CONST, 0.15f / C_U, 0.15f / C_U);  // lid, ldc.cu:378,391-456
+        snprintf(d->out_name, sizeof d->out_name, "lid");
+        break;
+    }
+    case LBM_CASE_POISEUILLE: {  // pos.cu:38-44,590
+        d->nx = d->ny = d->nz = 64;
+        const float C_U = 1.5441f;
+        d->tau = 0.58f, d->C_U = C_U, d->C_rho = 1060.f, d->CH = 0.0000655737f;
+        d->u_max = 0.15f / C_U;
+        set_bc(d, 2, LBM_BC_V, 1, +1, 1, LBM_SRC_PARABOLA, 0.09714700668f, 0.15f / C_U);
+        set_bc(d, 3, LBM_BC_V, 1, -1, 1, LBM_SRC_PARABOLA, 0.09714700668f, 0.15f / C_U);
+        snprintf(d->out_name, sizeof d->out_name, "pos");
+        break;
+    }
+    case LBM_CASE_GEO_Y_INOUT: {  // bif.cu:19-20,434
+        d->nx = 64, d->ny = 83, d->nz = 32;
+        d->tau = 0.55f, d->C_U = 0.24159041f, d->C_rho = 998.2f, d->CH = 0.000248925f;
+        set_bc(d, 2, LBM_BC_V, 1, +1, 1, LBM_SRC_PLANE_INLET, 0.0, 0.0);  // bif.cu:950-1021
+        set_bc(d, 3, LBM_BC_P, 1, -1, 1, LBM_SRC_CONST, 0.0, 0.0);         // bif.cu:877-948
+        snprintf(d->out_name, sizeof d->out_name, "bif");
+        break;
+    }
+    case LBM_CASE_GEO_OPENINGS: {  // cor.cu:19-20,302-306,717,796,871
+        d->nx = 291, d->ny = 291, d->nz = 372;
+        const float C_U = 2.74909090909091f;
+        d->tau = 0.55f, d->C_U = C_U, d->C_rho = 1060.f, d->CH = 6.1111e-05f;
+        d->geo_yfast = 1;
+        set_bc(d, 2, LBM_BC_VP, 0, +1, 0, LBM_SRC_CONST, (float)(0.1745 / C_U), 0.1745f / C_U);
+        set_bc(d, 3, LBM_BC_V, 0, -1, 0, LBM_SRC_CONST, (float)(0.1 / C_U), 0.1f / C_U);
+        for (int l = 5; l <= 7; l++) set_bc(d, l, LBM_BC_V, 2, -1, 2, LBM_SRC_CONST, (float)(0.02 / C_U), 0.02f / C_U);
+        set_open(d, 0, 3, 1, d->ny - 2, 1, d->nz - 2, 1);      // cor.cu:77-87
+        set_open(d, 0, 272, 1, d->ny - 2, 1, d->nz - 2, 2);    // cor.cu:89-101
+        set_open(d, 2, 185, 217, 236, 113, 137, 4);            // cor.cu:103-115
+        set_open(d, 2, 191, 160, 205, 159, 199, 5);            // cor.cu:117-129
+        set_open(d, 2, 204, 1, d->nx - 2, 1, d->ny - 2, 6);    // cor.cu:131-141
+        snprintf(d->out_name, sizeof d->out_name, "coronary");
+        break;
+    }
+    default:
+        return LBM_ERR_ARG;
+    }
+    d->z_begin = 0, d->z_end = d->nz;
+    return LBM_OK;
+}
+
+int lbm_create(const lbm_case_desc *desc, lbm_handle *out) {
+    using namespace lbm;
+    if (!desc || !out) {
+        g_create_error = "null argument";
+        return LBM_ERR_ARG;
+    }
+    *out = nullptr;
+    if (desc->struct_size != (int32_t)sizeof(lbm_case_desc)) {
+        g_create_error = fmt("lbm_case_desc size mismatch: caller %d, library %zu", desc->struct_size, sizeof(lbm_case_desc));
+        return LBM_ERR_ARG;
+    }
+    if (desc->nx < 5 || desc->ny < 6 || desc->nz < 5 || desc->case_rule < 0 || desc->case_rule > 3 ||
+        desc->z_begin < 0 || desc->z_end > desc->nz || desc->z_begin >= desc->z_end || desc->tau <= 0.5 ||
+        desc->n_bc < 0 || desc->n_bc > LBM_MAX_BC || desc->n_openings < 0 || desc->n_openings > LBM_MAX_OPENINGS ||
+        (desc->precision != LBM_F32 && desc->precision != LBM_F64)) {
+        g_create_error = "invalid case descriptor (dims >= 5, tau > 0.5, 0 <= z_begin < z_end <= nz)";
+        return LBM_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || desc->device >= ndev || desc->device < 0) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device: liblbm_b200 has no CPU path";
+        return LBM_ERR_NO_DEVICE;
+    }
+    SolverBase *s = nullptr;
+    int r;
+    if (desc->precision == LBM_F32) {
+        auto *p = new (std::nothrow) Solver<float>();
+        if (!p) return LBM_ERR_NOMEM;
+        p->d = *desc;
+        r = p->setup();
+        s = p;
+    } else {
+        auto *p = new (std::nothrow) Solver<double>();
+        if (!p) return LBM_ERR_NOMEM;
+        p->d = *desc;
+        r = p->setup();
+        s = p;
+    }
+    if (r) {
+        g_create_error = s->err;
+        delete s;
+        return r;
+    }
+    *out = new lbm_solver_s{s};
+    return LBM_OK;
+}
+
+int lbm_destroy(lbm_handle h) {
+    if (!h) return LBM_ERR_ARG;
+    delete h->s;
+    delete h;
+    return LBM_OK;
+}
+const char *lbm_last_error(lbm_handle h) { return h ? h->s->err.c_str() : lbm::g_create_error.c_str(); }
+
+#define H_OR_FAIL \
+    if (!h) return LBM_ERR_ARG
+
+int lbm_set_flag(lbm_handle h, const int32_t *f) { H_OR_FAIL; return h->s->set_flag(f); }
+int lbm_geo_pre(lbm_handle h) { H_OR_FAIL; return h->s->geo_pre(); }
+int lbm_index_transform(lbm_handle h, int64_t *n) { H_OR_FAIL; return h->s->index_transform(n); }
+int lbm_local_stored_count(lbm_handle h, int64_t *n) { H_OR_FAIL; return n ? h->s->local_stored_count(n) : LBM_ERR_ARG; }
+int lbm_set_compact_offset(lbm_handle h, int64_t off, int64_t total) { H_OR_FAIL; return h->s->set_compact_offset(off, total); }
+int lbm_read_vel(lbm_handle h) { H_OR_FAIL; return h->s->read_vel(); }
+int lbm_set_bc_planes(lbm_handle h, const float *a, const float *b) { H_OR_FAIL; return h->s->set_bc_planes(a, b); }
+int lbm_initialize(lbm_handle h) { H_OR_FAIL; return h->s->initialize(); }
+int lbm_step(lbm_handle h, int32_t n) { H_OR_FAIL; return h->s->step(n, nullptr); }
+int lbm_step_timed(lbm_handle h, int32_t n, float *ms) { H_OR_FAIL; return ms ? h->s->step(n, ms) : LBM_ERR_ARG; }
+int64_t lbm_step_count(lbm_handle h) { return h ? h->s->steps : -1; }
+int64_t lbm_launch_count(lbm_handle h) { return h ? h->s->launches : -1; }
+int lbm_residual(lbm_handle h, int32_t kind, double *v) { H_OR_FAIL; return v ? h->s->residual(kind, v) : LBM_ERR_ARG; }
+int lbm_get_geo(lbm_handle h, int32_t *g) { H_OR_FAIL; return g ? h->s->get_geo(g) : LBM_ERR_ARG; }
+int lbm_get_index(lbm_handle h, int32_t *g) { H_OR_FAIL; return g ? h->s->get_index(g) : LBM_ERR_ARG; }
+int lbm_get_fields(lbm_handle h, void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count) {
+    H_OR_FAIL;
+    return h->s->get_fields(rho, ux, uy, uz, first, count);
+}
+int lbm_debug_get_populations(lbm_handle h, void *f) { H_OR_FAIL; return f ? h->s->get_populations(f) : LBM_ERR_ARG; }
+int64_t lbm_num_fluid(lbm_handle h) { return h ? h->s->nfluid : -1; }
+int64_t lbm_device_bytes(lbm_handle h) { return h ? h->s->dev_bytes : -1; }
+int lbm_output_save(lbm_handle h, int32_t t) { H_OR_FAIL; return h->s->output_save(t); }
+int lbm_run_fixed(lbm_handle h, int32_t repeat, int32_t time_save, int32_t wf) { H_OR_FAIL; return h->s->run_fixed(repeat, time_save, wf); }
+int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max, int32_t time_save, int32_t wf,
+                     int32_t *its, double *res) {
+    H_OR_FAIL;
+    return h->s->run_converge(max_it, tol, stag_max, time_save, wf, its, res);
+}
+int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_t *bytes) {
+    H_OR_FAIL;
+    return h->s->halo_buffers(side, send, recv, bytes);
+}
+int lbm_step_begin(lbm_handle h, int32_t flags) { H_OR_FAIL; return h->s->step_begin(flags); }
+int lbm_step_end(lbm_handle h) { H_OR_FAIL; return h->s->step_end(); }
+int lbm_last_velsum(lbm_handle h, double *v) { H_OR_FAIL; return v ? h->s->last_velsum(v) : LBM_ERR_ARG; }
+void *lbm_stream(lbm_handle h) { return h ? h->s->stream_ptr() : nullptr; }
+int lbm_sync(lbm_handle h) { H_OR_FAIL; return h->s->sync(); }
+
+}  // extern "C"

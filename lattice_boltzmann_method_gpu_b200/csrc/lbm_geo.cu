@@ -1,0 +1,556 @@
+// Case pre-processing on the GPU: node labels (geo_pre), outer-wall-neighbour
+// marking, stream compaction (index_transform), node words for the fused step,
+// the initial equilibrium state (initialize), and the small gather / reduce /
+// halo kernels around the hot loop.
+//
+// Reference (serial host code): ldc.cu:468-580, Poiseulle.cu:52-382,
+// bifurcation.cu:36-427, coronary.cu:31-350.  All integer results are
+// bit-exact with it (tests compare against the CPU oracle).
+//
+// This file is compiled with -fmad=false: the initial state is written with the
+// reference's literal expression order so that STRICT runs start bit-identical.
+#include "lattice.cuh"
+#include "lbm_internal.h"
+
+namespace lbm {
+
+namespace {
+
+__host__ __device__ inline long long cell_of(const Box &b, int x, int y, int z) {
+    return (long long)x + (long long)b.px * ((long long)y + (long long)b.ny * (long long)(z - b.z0));
+}
+
+struct Coord {
+    int x, y, z;  // global
+};
+__device__ inline Coord coord_of(const Box &b, long long c) {
+    Coord r;
+    r.x = (int)(c % b.px);
+    long long t = c / b.px;
+    r.y = (int)(t % b.ny);
+    r.z = (int)(t / b.ny) + b.z0;
+    return r;
+}
+
+// binary voxel flag; 0 outside the global box, outside the held z range, or in the x padding
+__device__ inline int flag_at(const uint8_t *flag, const Box &b, int x, int y, int z) {
+    if (x < 0 || x >= b.nx || y < 0 || y >= b.ny || z < b.z0 || z >= b.z1 || z < 0 || z >= b.nz) return 0;
+    return flag[cell_of(b, x, y, z)];
+}
+__device__ inline int imin(int a, int b) { return a < b ? a : b; }
+__device__ inline int min6(const uint8_t *f, const Box &b, int x, int y, int z) {
+    int mx = imin(flag_at(f, b, x + 1, y, z), flag_at(f, b, x - 1, y, z));
+    int my = imin(flag_at(f, b, x, y - 1, z), flag_at(f, b, x, y + 1, z));
+    int mz = imin(flag_at(f, b, x, y, z - 1), flag_at(f, b, x, y, z + 1));
+    return imin(imin(mx, my), mz);
+}
+__device__ inline bool interior(const Box &b, int x, int y, int z) {
+    return x >= 1 && x <= b.nx - 2 && y >= 1 && y <= b.ny - 2 && z >= 1 && z <= b.nz - 2;
+}
+
+// Poiseuille binary field: disc in (x,z), float arithmetic (Poiseulle.cu:80-91)
+__global__ void k_make_flag_pos(uint8_t *flag, Box b) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.cells()) return;
+    Coord p = coord_of(b, c);
+    uint8_t v = 0;
+    if (p.x < b.nx && p.y >= 1 && p.y <= b.ny - 2) {
+        float radius = (b.nx - 1) / 2.0f, cx = (b.nx - 1) / 2.0f, cz = (b.nz - 1) / 2.0f;
+        float dx = p.x - cx, dz = p.z - cz;
+        float dist = sqrtf(dx * dx + dz * dz);
+        v = dist <= radius ? 1 : 0;
+    }
+    flag[c] = v;
+}
+
+// label before the inlet/outlet plane rules of the GEO_Y_INOUT case (bifurcation.cu:63-91)
+__device__ inline int bif_base(const uint8_t *f, const Box &b, int x, int y, int z) {
+    int g = flag_at(f, b, x, y, z);
+    bool xz_in = x >= 1 && x <= b.nx - 2 && z >= 1 && z <= b.nz - 2;
+    if (xz_in && (y == 0 || y == b.ny - 1)) g = 0;
+    if (xz_in && y >= 2 && y <= b.ny - 3) g += 3 * min6(f, b, x, y, z);
+    return g;
+}
+
+__global__ void k_labels(const uint8_t *flag, int32_t *label, Box b, GeoRules r) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.cells()) return;
+    Coord p = coord_of(b, c);
+    int g = 0;
+    if (p.x < b.nx) {
+        const int x = p.x, y = p.y, z = p.z;
+        if (r.case_rule == LBM_CASE_LDC) {
+            // ldc.cu:468-502: layers 0 / 1 / 3, lid 2 on y = NY-2
+            auto in = [&](int m) {
+                return x >= m && x <= b.nx - 1 - m && y >= m && y <= b.ny - 1 - m && z >= m && z <= b.nz - 1 - m;
+            };
+            g = in(2) ? 3 : (in(1) ? 1 : 0);
+            if (y == b.ny - 2 && x >= 1 && x <= b.nx - 2 && z >= 1 && z <= b.nz - 2) g = 2;
+        } else if (r.case_rule == LBM_CASE_POISEUILLE) {
+            // Poiseulle.cu:94-134
+            g = flag_at(flag, b, x, y, z);
+            bool xz_in = x >= 1 && x <= b.nx - 2 && z >= 1 && z <= b.nz - 2;
+            if (xz_in && y >= 2 && y <= b.ny - 3) g += 3 * min6(flag, b, x, y, z);
+            if (xz_in && (y == 1 || y == b.ny - 2)) {
+                int m4 = imin(imin(flag_at(flag, b, x + 1, y, z), flag_at(flag, b, x - 1, y, z)),
+                              imin(flag_at(flag, b, x, y, z - 1), flag_at(flag, b, x, y, z + 1)));
+                if (y == 1) g += m4;
+                if (y == b.ny - 2) g += 2 * m4;  // both apply if NY == 3; not a real case
+            }
+        } else if (r.case_rule == LBM_CASE_GEO_Y_INOUT) {
+            // bifurcation.cu:63-119
+            g = bif_base(flag, b, x, y, z);
+            bool xz_in = x >= 1 && x <= b.nx - 2 && z >= 1 && z <= b.nz - 2;
+            if (xz_in && y == 1) {
+                int g2 = bif_base(flag, b, x, 2, z);
+                g = g2 == 1 ? 1 : (g2 == 4 ? 2 : 0);
+            }
+            if (xz_in && y == b.ny - 2) {
+                // the reference copies from y = NY-3 *after* the inlet rule ran
+                int g2 = bif_base(flag, b, x, b.ny - 3, z);
+                if (b.ny - 3 == 1) {
+                    int g3 = bif_base(flag, b, x, 2, z);
+                    g2 = g3 == 1 ? 1 : (g3 == 4 ? 2 : 0);
+                }
+                g = g2 == 1 ? 1 : (g2 == 4 ? 3 : 0);
+            }
+        } else {
+            // coronary.cu:60-141
+            g = flag_at(flag, b, x, y, z);
+            if (interior(b, x, y, z)) g += 3 * min6(flag, b, x, y, z);
+            for (int k = 0; k < r.n_open; k++) {
+                const lbm_opening_rule &o = r.open[k];
+                int pc = o.axis == 0 ? x : (o.axis == 1 ? y : z);
+                int a = o.axis == 0 ? y : x;
+                int bb = o.axis == 2 ? y : z;
+                if (pc != o.coord || a < o.lo_a || a > o.hi_a || bb < o.lo_b || bb > o.hi_b) continue;
+                int m;
+                if (o.axis == 0)
+                    m = imin(imin(flag_at(flag, b, x, y - 1, z), flag_at(flag, b, x, y + 1, z)),
+                             imin(flag_at(flag, b, x, y, z - 1), flag_at(flag, b, x, y, z + 1)));
+                else if (o.axis == 1)
+                    m = imin(imin(flag_at(flag, b, x - 1, y, z), flag_at(flag, b, x + 1, y, z)),
+                             imin(flag_at(flag, b, x, y, z - 1), flag_at(flag, b, x, y, z + 1)));
+                else
+                    m = imin(imin(flag_at(flag, b, x, y - 1, z), flag_at(flag, b, x, y + 1, z)),
+                             imin(flag_at(flag, b, x - 1, y, z), flag_at(flag, b, x + 1, y, z)));
+                g += o.reps * m;
+            }
+        }
+    }
+    label[c] = g;
+}
+
+// Outer-wall-neighbour marking, gather form (Poiseulle.cu:138-254,
+// bifurcation.cu:123-239): a label-0 node becomes -1 when one of its 18
+// neighbours is a marking source lying inside [1,N-2]^3.  In place: only 0 -> -1
+// transitions happen and neither value is a source, so order does not matter.
+__global__ void k_mark(int32_t *label, Box b, GeoRules r) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.cells()) return;
+    Coord p = coord_of(b, c);
+    if (p.x >= b.nx || label[c] != 0) return;
+    bool hit = false;
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        int x = p.x + cxq(q), y = p.y + cyq(q), z = p.z + czq(q);
+        if (!interior(b, x, y, z) || z < b.z0 || z >= b.z1) continue;
+        int g = label[cell_of(b, x, y, z)];
+        if (g > 0 && g < 32 && ((r.mark_sources >> g) & 1u)) hit = true;
+    }
+    if (hit) label[c] = -1;
+}
+
+// ---------------------------------------------------------------- compaction
+// index_transform (Poiseulle.cu:257-271) as a three-kernel exclusive scan over
+// the array in memory order (= z,y,x; x-padding cells carry label 0).
+// "stored" = has an entry in the reference's compact arrays: label != 0, or -- for the LDC
+// rule, which stores the whole box (ldc.cu:54) -- any cell inside the box (not x padding).
+struct StoredRule {
+    int px, nx, all;
+};
+__device__ inline bool is_stored(const int32_t *label, long long c, StoredRule r) {
+    if (r.all) return (int)(c % r.px) < r.nx;
+    return label[c] != 0;
+}
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 16;  // cells per thread
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+__device__ inline int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[SCAN_BLOCK / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_BLOCK / 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < SCAN_BLOCK / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    int base = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[SCAN_BLOCK / 32 - 1];
+    __syncthreads();
+    return base + incl - v;
+}
+
+__global__ void k_tile_counts(const int32_t *label, long long cells, StoredRule sr, int32_t *tile_count) {
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        long long c = base + i;
+        if (c < cells && is_stored(label, c, sr)) cnt++;
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+}
+// single block: exclusive scan of the tile counts (carry across chunks); 64-bit totals
+__global__ void k_scan_tiles(const int32_t *tile_count, long long *tile_offset, int ntiles, long long *total_out) {
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int start = 0; start < ntiles; start += SCAN_BLOCK) {
+        int i = start + threadIdx.x;
+        int v = i < ntiles ? tile_count[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_offset[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void k_scatter_index(const int32_t *label, int32_t *index, long long cells, StoredRule sr,
+                                long long base_index, const long long *tile_offset) {
+    long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    int flags[SCAN_ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        long long c = base + i;
+        flags[i] = (c < cells && is_stored(label, c, sr)) ? 1 : 0;
+        cnt += flags[i];
+    }
+    int total;
+    int ex = block_exclusive_scan(cnt, &total);
+    long long run = base_index + tile_offset[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        long long c = base + i;
+        if (c < cells) {
+            index[c] = flags[i] ? (int32_t)run : -1;
+            run += flags[i];
+        }
+    }
+}
+
+__global__ void k_count_stored(const int32_t *label, long long cells, StoredRule sr, long long *out) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (c < cells && is_stored(label, c, sr)) ? 1 : 0;
+    unsigned m = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long *)out, (unsigned long long)__popc(m));
+}
+
+// ---------------------------------------------------------------- node words
+// One thread per cell of the state box.  Fluid nodes of the OWNED planes get
+// the 18 "source is not fluid" bits; everything else is NODE_SKIP.
+__global__ void k_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box b, int own_z0,
+                             int own_z1, int fluid_label, long long *nfluid) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = c < b.cells();
+    uint32_t w = NODE_SKIP;
+    if (valid) {
+        Coord p = coord_of(b, c);
+        int g = label[c];
+        label8[c] = (int8_t)g;
+        if (p.x < b.nx && g == fluid_label && p.z >= own_z0 && p.z < own_z1) {
+            w = 0;
+#pragma unroll
+            for (int q = 1; q < Q; q++) {
+                int x = p.x - cxq(q), y = p.y - cyq(q), z = p.z - czq(q);
+                bool inb = x >= 0 && x < b.nx && y >= 0 && y < b.ny && z >= b.z0 && z < b.z1;
+                int gs = inb ? label[cell_of(b, x, y, z)] : 0;
+                if (gs != fluid_label) w |= (1u << q);
+            }
+        }
+        node[c] = w;
+    }
+    unsigned fluid_m = __ballot_sync(0xffffffffu, valid && !(w & NODE_SKIP));
+    unsigned link_m = __ballot_sync(0xffffffffu, valid && (w & NODE_LINKS));
+    if ((threadIdx.x & 31) == 0 && valid) {
+        uint8_t k = fluid_m == 0 ? SEG_EMPTY : ((fluid_m == 0xffffffffu && link_m == 0) ? SEG_BULK : SEG_MIXED);
+        seg[c >> 5] = k;
+        if (fluid_m) atomicAdd((unsigned long long *)nfluid, (unsigned long long)__popc(fluid_m));
+    }
+}
+
+// ---------------------------------------------------------------- initialize
+template <typename T>
+__device__ inline T parabola_at(const Box &b, T umax, int x, int z) {
+    T cx = T(b.nx - 1) / T(2.0), cz = T(b.nz - 1) / T(2.0), r = T(b.nx - 1) / T(2.0);
+    T dx = T(x) - cx, dz = T(z) - cz;
+    return umax * (T(1.0) - (dx * dx + dz * dz) / (r * r));
+}
+
+// rho = 1, u = 0 on every cell; boundary planes / labels get their initial
+// velocity; f = feq(rho,u) into both buffers (ldc.cu:504-580, pos:273-382,
+// bif:329-427, cor:277-350).  Cells the reference does not store (label 0,
+// padding) are given the rest state, the value "static" links read.
+template <typename T>
+__global__ void k_init(const __grid_constant__ InitParams<T> p) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const Box &b = p.box;
+    if (c >= b.cells()) return;
+    Coord co = coord_of(b, c);
+    T rho = T(1.0), ux = T(0.0), uy = T(0.0), uz = T(0.0);
+    const int g = p.label[c];
+    const bool inbox = co.x < b.nx;
+    if (inbox) {
+        if (p.case_rule == LBM_CASE_LDC) {
+            if (co.y == b.ny - 1 || co.y == b.ny - 2) uz = p.u_max;  // ldc.cu:523-531
+        } else if (p.case_rule == LBM_CASE_POISEUILLE) {
+            if (g != 0 && (co.y <= 1 || co.y >= b.ny - 2)) uy = parabola_at<T>(b, p.u_max, co.x, co.z);  // pos:295-341
+        } else if (p.case_rule == LBM_CASE_GEO_Y_INOUT) {
+            if (g != 0 && co.y == 1) uy = p.plane_in[co.x + (long long)co.z * b.nx];  // bif:349-373
+            if (g != 0 && co.y == b.ny - 2) uy = p.plane_out[co.x + (long long)co.z * b.nx];
+        } else {
+            if (g >= 2 && g < LBM_MAX_BC && g != 4 && p.bc[g].kind != LBM_BC_NONE) {  // cor:302-306
+                T v = (T)p.bc[g].init_value;
+                if (p.bc[g].vaxis == 0) ux = v;
+                else if (p.bc[g].vaxis == 1) uy = v;
+                else uz = v;
+            }
+        }
+    }
+    T feq[Q];
+    if (p.case_rule == LBM_CASE_LDC) {
+        feq_all_ldc_init<T>(rho, ux, uy, uz, feq);
+    } else {
+        const T r3 = rho / T(3.0), r18 = rho / T(18.0), r36 = rho / T(36.0);
+#pragma unroll
+        for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        p.fa[(long long)q * p.qstride + c] = feq[q];
+        if (p.fb != p.fa) p.fb[(long long)q * p.qstride + c] = feq[q];
+    }
+    p.rho[c] = T(0), p.ux[c] = T(0), p.uy[c] = T(0), p.uz[c] = T(0);
+}
+
+// ---------------------------------------------------------------- gathers
+template <typename T>
+__global__ void k_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
+                                const int32_t *index, Box b, long long c0, long long c1, int fluid_label, long long first,
+                                T *orho, T *oux, T *ouy, T *ouz) {
+    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    int i = index[c];
+    if (i < 0) return;
+    long long o = (long long)i - first;
+    bool fl = label[c] == fluid_label;
+    orho[o] = fl ? rho[c] : T(0);
+    oux[o] = fl ? ux[c] : T(0);
+    ouy[o] = fl ? uy[c] : T(0);
+    ouz[o] = fl ? uz[c] : T(0);
+}
+template <typename T>
+__global__ void k_gather_pops(const T *f, long long qstride, const int32_t *index, long long c0, long long c1,
+                              long long first, long long count, T *out) {
+    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    int i = index[c];
+    if (i < 0) return;
+    long long o = (long long)i - first;
+    for (int q = 0; q < Q; q++) out[(long long)q * count + o] = f[(long long)q * qstride + c];
+}
+
+// kind 0: sum sqrt(u^2) over every stored entry (non-fluid entries are 0)    ldc.cu:460-466,662
+// kind 1: sum u^2 over fluid nodes of the trimmed box z[1,NZ-2] y[2,NY-3] x[1,NX-2]   bif:1158-1175
+template <typename T>
+__global__ void k_reduce_fields(const T *ux, const T *uy, const T *uz, const int32_t *label, Box b, long long c0,
+                                long long c1, int kind, int fluid_label, int case_rule, double *out) {
+    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (c < c1) {
+        int g = label[c];
+        Coord p = coord_of(b, c);
+        if (p.x < b.nx) {
+            T s = ux[c] * ux[c] + uy[c] * uy[c] + uz[c] * uz[c];
+            if (kind == 0) {
+                if (g == fluid_label) v = (double)(T)sqrt((double)s);
+            } else {
+                bool ok = case_rule == LBM_CASE_GEO_OPENINGS ? (g == 4) : (g >= 4);
+                if (case_rule == LBM_CASE_LDC) ok = g == fluid_label;
+                bool trimmed = p.x >= 1 && p.x <= b.nx - 2 && p.y >= 2 && p.y <= b.ny - 3 && p.z >= 1 && p.z <= b.nz - 2;
+                if (ok && trimmed) v = (double)s;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += ws[i];
+        if (t != 0.0) atomicAdd(out, t);
+    }
+}
+
+// ---------------------------------------------------------------- halo planes
+// side 0 (low-z face): the plane's populations with c_z = -1 leave; side 1: c_z = +1.
+__device__ inline int halo_q(int side, int k) {
+    const int up[5] = {5, 11, 13, 15, 16};    // c_z = +1
+    const int down[5] = {6, 12, 14, 17, 18};  // c_z = -1
+    return side ? up[k] : down[k];
+}
+template <typename T>
+__global__ void k_halo_pack(const T *f, long long qstride, Box b, int zl, int side, T *buf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.plane) return;
+    long long c = (long long)zl * b.plane + i;
+#pragma unroll
+    for (int k = 0; k < 5; k++) buf[(long long)k * b.plane + i] = f[(long long)halo_q(side, k) * qstride + c];
+}
+// `side` is the face of the RECEIVING slab: side 0 receives the c_z = +1 set into its low halo plane
+template <typename T>
+__global__ void k_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box b, int zl, int side,
+                              const T *buf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.plane) return;
+    long long c = (long long)zl * b.plane + i;
+    if (label8[c] != fluid_label) return;  // slots of solid halo nodes belong to the local fluid neighbour
+#pragma unroll
+    for (int k = 0; k < 5; k++) f[(long long)halo_q(1 - side, k) * qstride + c] = buf[(long long)k * b.plane + i];
+}
+
+inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+// ---------------------------------------------------------------- launchers
+cudaError_t launch_make_flag_pos(uint8_t *flag, Box ext, cudaStream_t s) {
+    k_make_flag_pos<<<nblocks(ext.cells(), 256), 256, 0, s>>>(flag, ext);
+    return cudaGetLastError();
+}
+cudaError_t launch_labels(const uint8_t *flag, int32_t *label, Box ext, GeoRules r, cudaStream_t s) {
+    k_labels<<<nblocks(ext.cells(), 256), 256, 0, s>>>(flag, label, ext, r);
+    return cudaGetLastError();
+}
+cudaError_t launch_mark(int32_t *label, Box ext, GeoRules r, cudaStream_t s) {
+    if (r.mark_sources == 0) return cudaSuccess;
+    k_mark<<<nblocks(ext.cells(), 256), 256, 0, s>>>(label, ext, r);
+    return cudaGetLastError();
+}
+size_t compact_scratch_ints(long long cells) {
+    long long ntiles = (cells + SCAN_TILE - 1) / SCAN_TILE;
+    return (size_t)(ntiles + 2 * ntiles + 4);  // int32 counts + int64 offsets
+}
+cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells, int px, int nx, int all,
+                           long long base, int32_t *scratch, size_t scratch_ints, long long *total_out_dev,
+                           cudaStream_t s) {
+    StoredRule sr{px, nx, all};
+    long long ntiles = (cells + SCAN_TILE - 1) / SCAN_TILE;
+    if ((size_t)(3 * ntiles + 4) > scratch_ints) return cudaErrorInvalidValue;
+    int32_t *counts = scratch;
+    // 8-byte aligned offsets behind the counts
+    long long *offsets = reinterpret_cast<long long *>(scratch + ((ntiles + 1) & ~1LL));
+    k_tile_counts<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, cells, sr, counts);
+    k_scan_tiles<<<1, SCAN_BLOCK, 0, s>>>(counts, offsets, (int)ntiles, total_out_dev);
+    k_scatter_index<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, index, cells, sr, base, offsets);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
+                                cudaStream_t s) {
+    StoredRule sr{px, nx, all};
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(long long), s);
+    if (e != cudaSuccess) return e;
+    k_count_stored<<<nblocks(cells, 256), 256, 0, s>>>(label, cells, sr, out_dev);
+    return cudaGetLastError();
+}
+cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box box, int own_z0,
+                              int own_z1, int fluid_label, long long *nfluid_dev, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(nfluid_dev, 0, sizeof(long long), s);
+    if (e != cudaSuccess) return e;
+    k_node_words<<<nblocks(box.cells(), 256), 256, 0, s>>>(label, node, seg, label8, box, own_z0, own_z1, fluid_label,
+                                                          nfluid_dev);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_init(const InitParams<T> &p, cudaStream_t s) {
+    k_init<T><<<nblocks(p.box.cells(), 128), 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
+                                 const int32_t *index, Box box, int own_z0, int own_z1, int fluid_label, long long first,
+                                 T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s) {
+    long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
+    if (c1 <= c0) return cudaSuccess;
+    k_gather_fields<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(rho, ux, uy, uz, label, index, box, c0, c1, fluid_label,
+                                                            first, orho, oux, ouy, ouz);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_gather_pops(const T *f, long long qstride, const int32_t *index, Box box, int own_z0, int own_z1,
+                               long long first, long long count, T *out, cudaStream_t s) {
+    long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
+    if (c1 <= c0) return cudaSuccess;
+    k_gather_pops<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(f, qstride, index, c0, c1, first, count, out);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_reduce_fields(const T *ux, const T *uy, const T *uz, const int32_t *label, Box box, int own_z0,
+                                 int own_z1, int kind, int fluid_label, int case_rule, double *out_dev, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
+    if (c1 <= c0) return cudaSuccess;
+    k_reduce_fields<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(ux, uy, uz, label, box, c0, c1, kind, fluid_label, case_rule,
+                                                            out_dev);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_halo_pack(const T *f, long long qstride, Box box, int zl, int side, T *buf, cudaStream_t s) {
+    k_halo_pack<T><<<nblocks(box.plane, 256), 256, 0, s>>>(f, qstride, box, zl, side, buf);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box box, int zl, int side,
+                               const T *buf, cudaStream_t s) {
+    k_halo_unpack<T><<<nblocks(box.plane, 256), 256, 0, s>>>(f, qstride, label8, fluid_label, box, zl, side, buf);
+    return cudaGetLastError();
+}
+
+#define LBM_INST(T)                                                                                                     \
+    template cudaError_t launch_init<T>(const InitParams<T> &, cudaStream_t);                                           \
+    template cudaError_t launch_gather_fields<T>(const T *, const T *, const T *, const T *, const int32_t *,           \
+                                                 const int32_t *, Box, int, int, int, long long, T *, T *, T *, T *,    \
+                                                 cudaStream_t);                                                         \
+    template cudaError_t launch_gather_pops<T>(const T *, long long, const int32_t *, Box, int, int, long long,         \
+                                               long long, T *, cudaStream_t);                                           \
+    template cudaError_t launch_reduce_fields<T>(const T *, const T *, const T *, const int32_t *, Box, int, int, int,  \
+                                                 int, int, double *, cudaStream_t);                                     \
+    template cudaError_t launch_halo_pack<T>(const T *, long long, Box, int, int, T *, cudaStream_t);                   \
+    template cudaError_t launch_halo_unpack<T>(T *, long long, const int8_t *, int, Box, int, int, const T *,           \
+                                               cudaStream_t);
+LBM_INST(float)
+LBM_INST(double)
+#undef LBM_INST
+
+}  // namespace lbm

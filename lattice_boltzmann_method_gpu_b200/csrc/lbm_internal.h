@@ -1,0 +1,115 @@
+// Internal declarations shared by the translation units of liblbm_b200.so.
+// Not installed; the public surface is include/lbm_b200.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/lbm_b200.h"
+
+namespace lbm {
+
+// node word ("link mask") of the fused kernels
+//   bit 0        : node is NOT a fluid node (skip)
+//   bit q (1..18): the source x - c_q of direction q is not a fluid node, so the
+//                  pulled value is one this node pushed itself last step
+constexpr int Q = 19;  // D3Q19
+constexpr uint32_t NODE_SKIP = 1u;
+constexpr uint32_t NODE_LINKS = 0x7FFFEu;
+
+// per 32-cell segment summary (one warp of the dense kernels)
+enum : uint8_t { SEG_BULK = 0, SEG_MIXED = 1, SEG_EMPTY = 2 };
+
+struct BcEntry {
+    int kind, naxis, nsign, vaxis, source, pulsatile;
+    double value, init_value;
+};
+
+// Geometry of a box of cells stored [z][y][x] with padded x pitch.
+struct Box {
+    int nx, ny, nz;   // GLOBAL dims (reference NX,NY,NZ)
+    int px;           // x pitch in cells (multiple of 32)
+    int z0, z1;       // global z range [z0,z1) held by this array
+    long long plane;  // px*ny
+    __host__ __device__ long long cells() const { return plane * (long long)(z1 - z0); }
+};
+
+struct GeoRules {
+    int case_rule;
+    int n_open;
+    lbm_opening_rule open[LBM_MAX_OPENINGS];
+    unsigned mark_sources;  // bit L set: label L is a marking source
+};
+
+// everything the fused step kernels need, passed by value as a __grid_constant__
+template <typename T>
+struct StepParams {
+    const T *src;
+    T *dst;
+    long long qstride;  // elements between consecutive populations
+    const uint32_t *node;
+    const uint8_t *seg;
+    const int8_t *label8;
+    T *rho, *ux, *uy, *uz;  // dense moments (written when MOMENTS)
+    double *resid;          // [1] accumulator of sum |u| (written when RESID)
+    Box box;                // state box
+    long long c_begin, c_end;  // cell range processed by this launch
+    int fluid_label;
+    T tau, inv_tau, om1;  // om1 = 1 - 1/tau
+    T pulse_scale;
+    BcEntry bc[LBM_MAX_BC];
+    const T *plane_in, *plane_out;  // nx * nz(global) each
+    int parity;                     // AA: 0 even (local) step, 1 odd (shifted) step
+};
+
+template <typename T>
+struct InitParams {
+    T *fa, *fb;  // both buffers (fb may equal fa for in-place storage)
+    long long qstride;
+    const int32_t *label;  // state box labels (int32)
+    T *rho, *ux, *uy, *uz;
+    Box box;
+    int case_rule;
+    T u_max;
+    BcEntry bc[LBM_MAX_BC];
+    const T *plane_in, *plane_out;
+};
+
+// ---- launchers implemented in the .cu files ----
+// geometry (lbm_geo.cu)
+cudaError_t launch_make_flag_pos(uint8_t *flag, Box ext, cudaStream_t s);
+cudaError_t launch_labels(const uint8_t *flag, int32_t *label, Box ext, GeoRules r, cudaStream_t s);
+cudaError_t launch_mark(int32_t *label, Box ext, GeoRules r, cudaStream_t s);
+// exclusive scan of (label != 0) over `cells` cells; index = running count + base, or -1
+cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells, int px, int nx, int all,
+                           long long base, int32_t *scratch, size_t scratch_ints, long long *total_out_dev,
+                           cudaStream_t s);
+size_t compact_scratch_ints(long long cells);
+cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
+                                cudaStream_t s);
+cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box box, int own_z0,
+                              int own_z1, int fluid_label, long long *nfluid_dev, cudaStream_t s);
+template <typename T>
+cudaError_t launch_init(const InitParams<T> &p, cudaStream_t s);
+template <typename T>
+cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
+                                 const int32_t *index, Box box, int own_z0, int own_z1, int fluid_label, long long first,
+                                 T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s);
+template <typename T>
+cudaError_t launch_gather_pops(const T *f, long long qstride, const int32_t *index, Box box, int own_z0, int own_z1,
+                               long long first, long long count, T *out, cudaStream_t s);
+template <typename T>
+cudaError_t launch_reduce_fields(const T *ux, const T *uy, const T *uz, const int32_t *label, Box box, int own_z0,
+                                 int own_z1, int kind, int fluid_label, int case_rule, double *out_dev, cudaStream_t s);
+template <typename T>
+cudaError_t launch_halo_pack(const T *f, long long qstride, Box box, int zl, int side, T *buf, cudaStream_t s);
+template <typename T>
+cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box box, int zl, int side,
+                               const T *buf, cudaStream_t s);
+
+// fused step (lbm_step_fast.cu / lbm_step_strict.cu)
+template <typename T>
+cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s);
+template <typename T>
+cudaError_t launch_step_dense_strict(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s);
+
+}  // namespace lbm

@@ -1,0 +1,12 @@
+// FAST arithmetic instantiation of the fused step (default nvcc FMA contraction).
+// This is the measured path.
+#include "step_dense.cuh"
+
+namespace lbm {
+template <typename T>
+cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s) {
+    return launch_step_dense_impl<T, false>(p, moments, resid, storage, s);
+}
+template cudaError_t launch_step_dense_fast<float>(const StepParams<float> &, bool, bool, int, cudaStream_t);
+template cudaError_t launch_step_dense_fast<double>(const StepParams<double> &, bool, bool, int, cudaStream_t);
+}  // namespace lbm

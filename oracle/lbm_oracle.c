@@ -303,6 +303,7 @@ typedef struct {
     REAL *src, *dst;      /* 19*nlat each, q-major (bif:1219-1220) */
     REAL *rho, *ux, *uy, *uz;
     REAL tau, u_max;
+    REAL u_bc; /* speed literal of the boundary kernel (pos:590); initialize uses u_max (pos:44) */
     REAL *inlety, *outlety; /* nx*nz planes (bif:1200-1203) */
     REAL cor_uin, cor_uout, cor_usub;
     double pulse_amp, pulse_period; /* extension: u_in(t) = u_in * (1 + A sin(2 pi t / T)) */
@@ -414,6 +415,7 @@ FN(orc_state) *FN(orc_create)(int case_id, int nx, int ny, int nz, const int32_t
     s->fluid_label = case_id == CASE_LDC ? 3 : 4;
     s->tau = (REAL)tau;
     s->u_max = (REAL)u_max;
+    s->u_bc = (REAL)u_max;
     s->geo = (int32_t *)malloc(nbox * sizeof(int32_t));
     s->index = (int32_t *)malloc(nbox * sizeof(int32_t));
     memcpy(s->geo, geo, nbox * sizeof(int32_t));
@@ -463,6 +465,7 @@ void FN(orc_set_bc_planes)(FN(orc_state) *s, const float *inlety, const float *o
 void FN(orc_set_cor_speeds)(FN(orc_state) *s, double uin, double uout, double usub) {
     s->cor_uin = (REAL)uin, s->cor_uout = (REAL)uout, s->cor_usub = (REAL)usub;
 }
+void FN(orc_set_u_bc)(FN(orc_state) *s, double u_bc) { s->u_bc = (REAL)u_bc; }
 void FN(orc_set_pulse)(FN(orc_state) *s, double amp, double period) {
     s->pulse_amp = amp, s->pulse_period = period;
 }
@@ -637,11 +640,11 @@ static void boundary_stream(FN(orc_state) *s) {
         REAL up = R(0.0);
         switch (s->case_id) {
         case CASE_LDC: /* lid, ldc:391-456 */
-            if (g == 2) set = SET_YM, kind = 0, vaxis = 2, up = s->u_max;
+            if (g == 2) set = SET_YM, kind = 0, vaxis = 2, up = s->u_bc;
             break;
         case CASE_POS: /* pos:748-891; u at the BC node's own (i,k), pos:597 */
-            if (g == 3) set = SET_YM, kind = 0, vaxis = 1, up = parabola(s, s->u_max, x, z);
-            if (g == 2) set = SET_YP, kind = 0, vaxis = 1, up = parabola(s, s->u_max, x, z);
+            if (g == 3) set = SET_YM, kind = 0, vaxis = 1, up = parabola(s, s->u_bc, x, z);
+            if (g == 2) set = SET_YP, kind = 0, vaxis = 1, up = parabola(s, s->u_bc, x, z);
             break;
         case CASE_BIF: /* outlet P bif:877-948, inlet V bif:950-1021 */
             if (g == 3) set = SET_YM, kind = 1;

@@ -82,6 +82,7 @@ def _declare(L: C.CDLL) -> None:
         g("orc_set_bc_planes").argtypes = [C.c_void_p, _f32p, _f32p]
         g("orc_set_cor_speeds").argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         g("orc_set_pulse").argtypes = [C.c_void_p, C.c_double, C.c_double]
+        g("orc_set_u_bc").argtypes = [C.c_void_p, C.c_double]
         g("orc_initialize").argtypes = [C.c_void_p]
         g("orc_step").argtypes = [C.c_void_p, C.c_int]
         g("orc_get_fields").argtypes = [C.c_void_p, rp, rp, rp, rp]
@@ -182,6 +183,9 @@ class Oracle:
 
     def set_cor_speeds(self, uin, uout, usub):
         self._fn("orc_set_cor_speeds")(self._h, uin, uout, usub)
+
+    def set_u_bc(self, u_bc):
+        self._fn("orc_set_u_bc")(self._h, float(u_bc))
 
     def set_pulse(self, amp, period):
         self._fn("orc_set_pulse")(self._h, amp, period)

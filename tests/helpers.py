@@ -1,0 +1,153 @@
+"""Shared builders for the parity tests: the same case set up on the CPU oracle and (on a GPU
+box) on the CUDA library through its C ABI."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from oracle import oracle as O
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+LDC_UMAX = float(np.float32(0.15) / np.float32(2.4705))          # ldc.cu:52
+POS_UMAX = float(np.float32(0.15) / np.float32(1.5441))          # pos.cu:44 (initialize)
+POS_UBC = float(np.float32(0.09714700668))                       # pos.cu:590 (boundary kernel literal)
+TAU_LDC = float(np.float32(0.55))
+TAU_POS = float(np.float32(0.58))
+
+
+def bif_flag():
+    bits = np.load(GOLDEN / "bif_flag_bits.npy")
+    return np.unpackbits(bits)[: 64 * 83 * 32].astype(np.int32).reshape(32, 83, 64)
+
+
+def bif_bc_planes(shipped_order=False):
+    """(inlet, outlet) raw planes.  The shipped bc.txt holds the inlet profile in its SECOND plane
+    (so code + data as shipped give a zero inlet); the default fixture moves it first."""
+    bc = np.load(GOLDEN / "bif_bc.npy")
+    return (bc[0], bc[1]) if shipped_order else (bc[1], bc[2])
+
+
+def synthetic_openings_mask(nx=40, ny=36, nz=44):
+    """A small vessel for the GEO_OPENINGS (coronary) rule: a tube along +x cut at x=3 (inlet) and
+    x=nx-5 (main outlet), with a side branch rising in +z that is cut at z=ztop (sub-exit)."""
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    cy, cz, r = ny / 2 - 0.5, nz / 3.0, 6.3
+    x1, ztop = nx - 5, nz - 6
+    tube = ((y - cy) ** 2 + (z - cz) ** 2 <= r * r) & (x >= 3) & (x <= x1)
+    bx, rb = nx / 2.0, 4.4
+    branch = ((x - bx) ** 2 + (y - cy) ** 2 <= rb * rb) & (z >= cz) & (z <= ztop)
+    flag = (tube | branch).astype(np.int32)
+    rules = np.array(
+        [
+            [0, 3, 1, ny - 2, 1, nz - 2, 1],
+            [0, x1, 1, ny - 2, 1, nz - 2, 2],
+            [2, ztop, int(bx - 8), int(bx + 8), int(cy - 8), int(cy + 8), 4],
+        ],
+        dtype=np.int32,
+    )
+    return flag, rules
+
+
+COR_SPEEDS = dict(uin=0.02, uout=0.012, usub=0.004)
+
+
+def oracle_case(name, n=None, dtype=np.float32, pulse=None, shipped_bc=False):
+    """Returns (Oracle, geo, index, nlat)."""
+    if name == "ldc":
+        geo = O.geo_pre_ldc(n, n, n)
+        idx, nlat = O.index_dense(geo.shape)
+        o = O.Oracle(O.CASE_LDC, geo, idx, nlat, TAU_LDC, LDC_UMAX, dtype=dtype)
+    elif name == "pos":
+        geo = O.geo_pre_pos(n, n, n)
+        idx, nlat = O.index_transform(geo)
+        o = O.Oracle(O.CASE_POS, geo, idx, nlat, TAU_POS, POS_UMAX, dtype=dtype)
+        o.set_u_bc(POS_UBC)
+    elif name == "bif":
+        geo = O.geo_pre_bif(bif_flag())
+        idx, nlat = O.index_transform(geo)
+        o = O.Oracle(O.CASE_BIF, geo, idx, nlat, TAU_LDC, 0.0, dtype=dtype)
+        inl, out = bif_bc_planes(shipped_bc)
+        nz, ny, nx = geo.shape
+        inl = np.where(geo[:, 1, :] == 2, inl, 0).astype(np.float32)
+        out = np.where(geo[:, ny - 2, :] == 3, out, 0).astype(np.float32)
+        o.set_bc_planes(inl, out)
+        if pulse:
+            o.set_pulse(*pulse)
+    elif name == "cor":
+        flag, rules = synthetic_openings_mask()
+        geo = O.geo_pre_cor(flag, rules)
+        idx, nlat = O.index_transform(geo)
+        o = O.Oracle(O.CASE_COR, geo, idx, nlat, TAU_LDC, 0.0, dtype=dtype)
+        o.set_cor_speeds(COR_SPEEDS["uin"], COR_SPEEDS["uout"], COR_SPEEDS["usub"])
+        if pulse:
+            o.set_pulse(*pulse)
+    else:
+        raise ValueError(name)
+    o.initialize()
+    return o, geo, idx, nlat
+
+
+def gpu_case(name, n=None, precision=None, math_mode=None, pulse=None, shipped_bc=False, z_range=None,
+             storage=None):
+    """The same case on the CUDA library, driven through the reference-named call sequence."""
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    precision = L.F32 if precision is None else precision
+    math_mode = L.MATH_FAST if math_mode is None else math_mode
+    storage = L.STORE_DENSE_AB if storage is None else storage
+    if name == "ldc":
+        d = L.case_defaults(L.CASE_LDC)
+        d.nx = d.ny = d.nz = n
+    elif name == "pos":
+        d = L.case_defaults(L.CASE_POISEUILLE)
+        d.nx = d.ny = d.nz = n
+    elif name == "bif":
+        d = L.case_defaults(L.CASE_GEO_Y_INOUT)
+    elif name == "cor":
+        flag, rules = synthetic_openings_mask()
+        d = L.case_defaults(L.CASE_GEO_OPENINGS)
+        d.nz, d.ny, d.nx = flag.shape
+        d.n_openings = len(rules)
+        for i, r in enumerate(rules):
+            o = d.openings[i]
+            o.axis, o.coord, o.lo_a, o.hi_a, o.lo_b, o.hi_b, o.reps = (int(v) for v in r)
+        vals = {2: COR_SPEEDS["uin"], 3: COR_SPEEDS["uout"], 5: COR_SPEEDS["usub"], 6: COR_SPEEDS["usub"],
+                7: COR_SPEEDS["usub"]}
+        for i in range(d.n_bc):
+            d.bc[i].value = d.bc[i].init_value = vals[d.bc[i].label]
+    else:
+        raise ValueError(name)
+    d.z_begin, d.z_end = (0, d.nz) if z_range is None else z_range
+    d.precision, d.math, d.storage = precision, math_mode, storage
+    if pulse:
+        d.pulse_amp, d.pulse_period = pulse
+        for i in range(d.n_bc):
+            if d.bc[i].label == 2:
+                d.bc[i].pulsatile = 1
+    c = L.Case(d)
+    if name == "bif":
+        c.set_flag(bif_flag())
+    if name == "cor":
+        c.set_flag(synthetic_openings_mask()[0])
+    return c
+
+
+def gpu_setup(c, name, shipped_bc=False):
+    """geo_pre -> index_transform -> read_vel -> initialize, like the reference's main()."""
+    c.geo_pre()
+    nlat = c.index_transform()
+    if name == "bif":
+        c.set_bc_planes(*bif_bc_planes(shipped_bc))
+    c.initialize()
+    return nlat
+
+
+def rel_err(got, ref):
+    """max |got-ref| over rho,ux,uy,uz, velocity components relative to max|u|, rho relative to 1"""
+    scale = max(float(np.abs(r).max()) for r in ref[1:])
+    scale = scale if scale > 0 else 1.0
+    e_u = max(float(np.abs(g.astype(np.float64) - r.astype(np.float64)).max()) for g, r in zip(got[1:], ref[1:]))
+    e_r = float(np.abs(got[0].astype(np.float64) - ref[0].astype(np.float64)).max())
+    return max(e_u / scale, e_r)

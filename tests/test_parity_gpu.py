@@ -1,0 +1,153 @@
+"""GPU: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): geo / index tables bit-exact; density and velocity within
+1e-12 (fp64) / 1e-5 (fp32), velocities relative to max|u|, after N steps.  In STRICT arithmetic the
+kernel keeps the reference's expression order and must agree with the oracle to the last bit."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("ldc", 24), ("ldc", 33), ("pos", 24), ("bif", None), ("cor", None)]
+
+
+def L():
+    import lattice_boltzmann_method_gpu_b200 as lib
+
+    return lib
+
+
+@pytest.mark.parametrize("name,n", CASES + [("pos", 37)])
+def test_geo_and_index_bit_exact(name, n):
+    _, geo, idx, nlat = H.oracle_case(name, n)
+    c = H.gpu_case(name, n)
+    c.geo_pre()
+    assert c.index_transform() == nlat
+    assert np.array_equal(c.get_geo(), geo)
+    assert np.array_equal(c.get_index(), idx)
+    fluid = 3 if name == "ldc" else 4
+    assert c.num_fluid == int((geo == fluid).sum())
+
+
+@pytest.mark.parametrize("name,n", CASES)
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_strict_fields_bit_exact(name, n, prec):
+    lib = L()
+    dt = np.float32 if prec == "f32" else np.float64
+    o, geo, idx, nlat = H.oracle_case(name, n, dt)
+    c = H.gpu_case(name, n, lib.F32 if prec == "f32" else lib.F64, lib.MATH_STRICT)
+    H.gpu_setup(c, name)
+    for nsteps in (1, 2, 37):
+        o.step(nsteps)
+        c.step(nsteps)
+        ref, got = o.fields(), c.get_fields()
+        for r, g, nm in zip(ref, got, ("rho", "ux", "uy", "uz")):
+            assert np.array_equal(r, g), f"{name} {prec} {nm} differs after +{nsteps} steps: {np.abs(r - g).max()}"
+
+
+@pytest.mark.parametrize("name,n", CASES)
+def test_strict_populations_bit_exact(name, n):
+    """every slot a fluid node will pull next step equals the oracle's d_scr"""
+    lib = L()
+    o, geo, idx, nlat = H.oracle_case(name, n, np.float64)
+    c = H.gpu_case(name, n, lib.F64, lib.MATH_STRICT)
+    H.gpu_setup(c, name)
+    o.step(9)
+    c.step(9)
+    fo, fg = o.populations(), c.get_populations()
+    from oracle import oracle as O
+
+    fluid = 3 if name == "ldc" else 4
+    zz, yy, xx = np.nonzero(geo == fluid)
+    for q in range(19):
+        src = idx[zz - O.CZ[q], yy - O.CY[q], xx - O.CX[q]]
+        assert (src >= 0).all()
+        assert np.array_equal(fo[q, src], fg[q, src]), f"direction {q}"
+
+
+@pytest.mark.parametrize("name,n,steps", [("ldc", 32, 400), ("pos", 24, 400), ("bif", None, 400), ("cor", None, 300)])
+@pytest.mark.parametrize("prec,tol", [("f32", 1e-5), ("f64", 1e-12)])
+def test_fast_fields_within_tolerance(name, n, steps, prec, tol):
+    lib = L()
+    dt = np.float32 if prec == "f32" else np.float64
+    o, geo, idx, nlat = H.oracle_case(name, n, dt)
+    c = H.gpu_case(name, n, lib.F32 if prec == "f32" else lib.F64, lib.MATH_FAST)
+    H.gpu_setup(c, name)
+    o.step(steps)
+    c.step(steps)
+    err = H.rel_err(c.get_fields(), o.fields())
+    assert err <= tol, f"{name} {prec}: rel err {err:.3e} > {tol}"
+
+
+def test_shipped_bc_gives_rest_state():
+    # code + data as shipped: inlet plane is all zero -> fluid stays at rest
+    lib = L()
+    c = H.gpu_case("bif", None, lib.F32, lib.MATH_STRICT, shipped_bc=True)
+    H.gpu_setup(c, "bif", shipped_bc=True)
+    c.step(25)
+    rho, ux, uy, uz = c.get_fields()
+    assert not ux.any() and not uy.any() and not uz.any()
+
+
+@pytest.mark.parametrize("name", ["bif", "cor"])
+def test_pulsatile_inlet_matches_extended_oracle(name):
+    # no reference code exists for the unsteady inlet: parity is against the oracle's own extension
+    lib = L()
+    pulse = (0.3, 40.0)
+    o, *_ = H.oracle_case(name, None, np.float64, pulse=pulse)
+    c = H.gpu_case(name, None, lib.F64, lib.MATH_STRICT, pulse=pulse)
+    H.gpu_setup(c, name)
+    o.step(61)
+    c.step(30)
+    c.step(31)
+    for r, g in zip(o.fields(), c.get_fields()):
+        assert np.array_equal(r, g)
+
+
+def test_residual_reductions():
+    lib = L()
+    o, geo, idx, nlat = H.oracle_case("ldc", 24, np.float64)
+    c = H.gpu_case("ldc", 24, lib.F64, lib.MATH_STRICT)
+    H.gpu_setup(c, "ldc")
+    o.step(20)
+    c.step(20)
+    assert abs(c.residual(lib.RES_VELSUM) - o.velsum()) <= 1e-12 * o.velsum()
+    o, geo, idx, nlat = H.oracle_case("bif", None, np.float32)
+    c = H.gpu_case("bif", None, lib.F32, lib.MATH_STRICT)
+    H.gpu_setup(c, "bif")
+    o.step(20)
+    c.step(20)
+    assert abs(c.calc_res() - o.calc_res()) <= 1e-6 * o.calc_res()
+
+
+def test_poiseuille_matches_analytic_profile():
+    lib = L()
+    n = 32
+    c = H.gpu_case("pos", n, lib.F64, lib.MATH_FAST)
+    H.gpu_setup(c, "pos")
+    c.step(3000)
+    uy = c.get_fields()[2]
+    geo, idx = c.get_geo(), c.get_index()
+    z, x = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    cc = (n - 1) / 2
+    ana = H.POS_UBC * (1 - ((x - cc) ** 2 + (z - cc) ** 2) / cc ** 2)
+    fl = geo[:, n // 2, :] == 4
+    got = uy[idx[:, n // 2, :][fl]]
+    err = got - ana[fl]
+    # staircase wall: the error sits in the outermost ring of nodes; the
+    # thesis' "< 2 %" (section 4.9.2) holds for the centre-line speed and the volumetric flux
+    assert abs(got.max() - ana[fl].max()) / ana[fl].max() < 0.02
+    assert abs(got.sum() - ana[fl].sum()) / ana[fl].sum() < 0.02
+    assert np.abs(err).mean() / H.POS_UBC < 0.05
+
+
+def test_call_order_is_enforced():
+    lib = L()
+    c = H.gpu_case("ldc", 16)
+    with pytest.raises(lib.LbmError):
+        c.initialize()
+    c.geo_pre()
+    with pytest.raises(lib.LbmError):
+        c.step(1)
