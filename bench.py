@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Headline benchmark: MLUPS of the fused D3Q19 BGK step and its HBM-roofline fraction.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--n 512] [--precision f64|f32] [--storage ab|aa] [--no-e2e] [--no-cpu]
+
+Workload (BASELINE.json configs[2]): dense lid-driven cavity 512^3, fp64, one B200.
+At N > 1 (torchrun, one rank per GPU) the domain is 512 x 512 x (512*N), z-slab sharded, one
+512^3 slab per GPU (weak scaling), halo exchange of the 5 crossing populations per face over NCCL.
+
+A "step" is one pass of the hot path: one fused pull-stream + collide (+ link-wise boundaries)
+launch over every fluid node.  `value` = fluid-node updates / s / 1e6 with all state resident in HBM,
+timed with CUDA events on the library's own stream (max over ranks).  `e2e` = the same metric for
+one save interval of the reference's main loop driven through the C ABI from host memory: K steps
+followed by the D2H copy of rho,ux,uy,uz into pinned host buffers (ldc.cu:669-675), plus -- once,
+inside the timed region -- create / geo_pre / index_transform / initialize.
+Algorithmic traffic: 2 x 19 x sizeof(real) bytes per fluid-node update.
+
+--impl reference times the CPU restatement of the reference's loop (oracle/, all host threads)
+on a bounded sample of the same workload; the reference itself is a CUDA program with the grid
+size compiled in (64^3, fp32), so its own binary (oracle/_ref/ldc_ref) is reported separately
+under "reference_cuda" when present.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+BYTES_PER_LU = {"f64": 304, "f32": 152}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2])), power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def oracle_threads(n):
+    import ctypes
+
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except Exception:
+        pass
+
+
+def cpu_oracle_mlups(n, precision, steps, threads):
+    """the oracle's literal update + boundary_stream loop on the host cores"""
+    from oracle import oracle as O
+
+    oracle_threads(threads)
+    geo = O.geo_pre_ldc(n, n, n)
+    idx, nlat = O.index_dense(geo.shape)
+    dt = np.float64 if precision == "f64" else np.float32
+    o = O.Oracle(O.CASE_LDC, geo, idx, nlat, float(np.float32(0.55)), float(np.float32(0.15) / np.float32(2.4705)), dtype=dt)
+    o.initialize()
+    o.step(1)
+    t = o.time_steps(steps)
+    return o.num_fluid() * steps / t / 1e6, t
+
+
+def reference_cuda_line():
+    """MLUPS of the unmodified reference program on this GPU (64^3 fp32, its own cudaEvent span,
+    residual reduce + per-kernel syncs + VTK dumps included: that IS the reference's loop)."""
+    exe = ROOT / "oracle" / "_ref" / "ldc_ref"
+    if not exe.exists():
+        return None
+    import tempfile
+
+    try:
+        with tempfile.TemporaryDirectory() as wd:
+            os.makedirs(os.path.join(wd, "out"))
+            r = subprocess.run([str(exe)], cwd=wd, capture_output=True, text=True, timeout=300)
+            m = re.search(r"TOTAL RUNNING TIME: ([0-9.eE+-]+) MILLI", r.stdout)
+            its = [int(v) for v in re.findall(r"lid_(\d+)\.vtk", " ".join(os.listdir(os.path.join(wd, "out"))))]
+            if not m or not its:
+                return None
+            ms, k = float(m.group(1)), max(its)
+            return {"program": "Lid_driven_cavity/ldc.cu (unmodified, nvcc sm_100a)", "grid": "64^3 fp32",
+                    "iterations": k, "total_ms": ms, "mlups_fluid": 60 ** 3 * k / (ms * 1e-3) / 1e6,
+                    "mlups_all_nodes": 64 ** 3 * k / (ms * 1e-3) / 1e6}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_n
+    # W warm-up + exactly K timed steps of the bounded sample
+    from oracle import oracle as O
+
+    oracle_threads(threads)
+    geo = O.geo_pre_ldc(n, n, n)
+    idx, nlat = O.index_dense(geo.shape)
+    dt = np.float64 if args.precision == "f64" else np.float32
+    o = O.Oracle(O.CASE_LDC, geo, idx, nlat, float(np.float32(0.55)), float(np.float32(0.15) / np.float32(2.4705)), dtype=dt)
+    o.initialize()
+    o.step(args.warmup)
+    t = o.time_steps(args.steps)
+    val = o.num_fluid() * args.steps / t / 1e6
+    sample = f"LDC {n}^3 {args.precision} (bounded sample of the {args.n}^3 workload), {args.steps} steps, oracle port of ldc.cu:57-458"
+    line = {
+        "impl": "reference", "metric": "MLUPS", "value": val, "unit": "MLUPS (fluid-node updates/s/1e6)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": val, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    n = args.n
+    return {"workload": f"dense lid-driven cavity {n}x{n}x{n * world} D3Q19 BGK {args.precision}, tau=0.55, Re~222 (ldc.cu rules), "
+                        f"{n}^3 per GPU z-slab",
+            "storage": args.storage, "math": "fast", "bytes_per_node_update": BYTES_PER_LU[args.precision],
+            "parallelism": f"zslab{world}", "l2_policy": "working set (>=20 GB) far exceeds the 126 MB L2; no flush needed"}
+
+
+def run_ours(args):
+    import torch
+
+    import lattice_boltzmann_method_gpu_b200 as L
+    from lattice_boltzmann_method_gpu_b200 import slab
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.n
+    prec = L.F64 if args.precision == "f64" else L.F32
+    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage]
+    dtype = np.float64 if args.precision == "f64" else np.float32
+
+    def build_case():
+        d = L.case_defaults(L.CASE_LDC)
+        d.nx, d.ny, d.nz = n, n, n * world
+        d.z_begin, d.z_end = rank * n, (rank + 1) * n
+        d.precision, d.storage, d.math, d.device = prec, storage, L.MATH_FAST, local
+        return slab.SlabCase(d) if world > 1 else L.Case(d)
+
+    def setup(c):
+        if world > 1:
+            c.setup()
+        else:
+            c.geo_pre()
+            c.index_transform()
+            c.initialize()
+
+    c = build_case()
+    setup(c)
+    nfluid_local = c.num_fluid
+    nfluid = nfluid_local
+    if world > 1:
+        t_ = torch.tensor([nfluid_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t_)
+        nfluid = int(t_.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up, exactly K timed steps, CUDA events, max over ranks
+    c.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = c.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    ms = c.step_timed(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = c.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms = float(t_.item())
+        l_ = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(l_)
+        launches = int(l_.item())
+    value = nfluid * args.steps / (ms * 1e-3) / 1e6
+
+    # the dominant kernel alone (rank 0's slab), CUDA events on the launching stream
+    bpl = BYTES_PER_LU[args.precision]
+    k_ms = ms / args.steps  # one launch per step (plus face launches at N>1, same kernel)
+    achieved = nfluid_local * bpl / (k_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end to end through the C ABI from host memory
+    e2e = None
+    if not args.no_e2e:
+        c.close()
+        del c
+        torch.cuda.empty_cache()
+        nstored = n * n * n  # LDC stores every node of the slab
+        pinned = [torch.empty(nstored, dtype=torch.float64 if args.precision == "f64" else torch.float32).pin_memory()
+                  for _ in range(4)]
+        outs = [p.numpy() for p in pinned]
+        barrier()
+        t0 = time.perf_counter()
+        c = build_case()
+        setup(c)
+        c.step(args.steps)
+        c.get_fields(outs)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t_ = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            t_e2e = float(t_.item())
+        e2e = {"value": nfluid * args.steps / t_e2e / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(__import__("ctypes").sizeof(L.CaseDesc) / args.steps),
+               "d2h_bytes_per_step": int(world * 4 * nstored * outs[0].itemsize / args.steps),
+               "what": f"create+geo_pre+index_transform+initialize, {args.steps} steps, D2H of rho,ux,uy,uz into pinned host buffers; "
+                       "the case is described by a 4.7 KB descriptor (the LDC mask is analytic, ldc.cu:468-502), so H2D is only that",
+               "seconds": t_e2e}
+        assert float(np.abs(outs[3]).max()) > 0.0
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cn, csteps = args.cpu_n, args.cpu_steps
+            v, t = cpu_oracle_mlups(cn, args.precision, csteps, 1)
+            cpu = {"value": v, "unit": "MLUPS", "cores": 1, "kind": "port",
+                   "sample": f"LDC {cn}^3 {args.precision}, {csteps} steps ({t:.1f} s) of the oracle's serial update+boundary_stream loop; "
+                             f"host has {os.cpu_count()} cores"}
+        line = {
+            "metric": "MLUPS", "value": value, "unit": "MLUPS (fluid-node updates/s/1e6)", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": args.traffic_bytes, "peak_source": peak_src,
+                         "kernel": "k_step_dense_ab", "algorithmic_bytes_per_launch": nfluid_local * bpl,
+                         "frac_of_spec_8TBs": achieved / 8000.0},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "wall_ms_per_step": wall / args.steps * 1e3, "fluid_nodes": int(nfluid),
+            "mlups_all_nodes": value * (n ** 3 * world) / nfluid,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_cpu:
+            rc = reference_cuda_line()
+            if rc:
+                line["reference_cuda"] = rc
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=512)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--storage", default="ab", choices=["ab", "aa"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=25)
+    ap.add_argument("--ref-n", type=int, default=160)
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram__bytes_read.sum+dram__bytes_write.sum per launch from the committed ncu capture")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -220,13 +220,16 @@ int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max,
  * staging buffers of that side (5 * nx_pitch * ny reals) for the caller's
  * transport (NCCL send/recv, or a peer GPU's kernel storing straight into it).
  * lbm_step_begin .. lbm_step_end bracket one step:
- *   begin: face planes computed first, send buffers packed (async on stream)
- *   <caller exchanges send->recv buffers of neighbouring handles>
- *   end:   received populations unpacked into the halo planes, buffers swap. */
+ *   begin:    face planes computed first, send buffers packed (async on the handle's stream)
+ *   <caller posts the transfers send->recv between neighbouring handles on its transport stream>
+ *   interior: the remaining planes, overlapping the transfer (implied by end if omitted)
+ *   <caller makes the handle's stream wait for the transfers>
+ *   end:      received populations unpacked into the halo planes, buffers swap. */
 int lbm_halo_buffers(lbm_handle h, int32_t side, void **send_dev, void **recv_dev, size_t *bytes);
 #define LBM_STEP_MOMENTS 1 /* materialise rho,u on this step (bif:592-595) */
 #define LBM_STEP_VELSUM 2  /* also accumulate S = sum|u| for lbm_last_velsum (ldc:660-662) */
 int lbm_step_begin(lbm_handle h, int32_t flags);
+int lbm_step_interior(lbm_handle h);
 int lbm_step_end(lbm_handle h);
 /* S of the most recent step run with LBM_STEP_VELSUM (this slab's share) */
 int lbm_last_velsum(lbm_handle h, double *value);

@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "lbm_initialize", "lbm_step", "lbm_step_timed", "lbm_step_count", "lbm_launch_count", "lbm_residual",
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
     "lbm_device_bytes", "lbm_output_save", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
-    "lbm_step_begin", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
+    "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
 ]
 
 _lib = None
@@ -123,6 +123,7 @@ def load_library() -> C.CDLL:
         "lbm_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
         "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t)], C.c_int),
         "lbm_step_begin": ([vp, i32], C.c_int),
+        "lbm_step_interior": ([vp], C.c_int),
         "lbm_step_end": ([vp], C.c_int),
         "lbm_last_velsum": ([vp, P(dbl)], C.c_int),
         "lbm_stream": ([vp], vp),
@@ -235,6 +236,9 @@ class Case:
 
     def step_begin(self, flags: int = 0):
         self._ck(self._L.lbm_step_begin(self._h, flags))
+
+    def step_interior(self):
+        self._ck(self._L.lbm_step_interior(self._h))
 
     def step_end(self):
         self._ck(self._L.lbm_step_end(self._h))

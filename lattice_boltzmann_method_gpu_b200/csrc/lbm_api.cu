@@ -46,6 +46,7 @@ struct SolverBase {
     virtual int initialize() = 0;
     virtual int step(int n, float *ms) = 0;
     virtual int step_begin(int flags) = 0;
+    virtual int step_interior() = 0;
     virtual int step_end() = 0;
     virtual int last_velsum(double *v) = 0;
     virtual int residual(int kind, double *v) = 0;
@@ -112,6 +113,8 @@ struct Solver final : SolverBase {
     bool offset_set = false;
     size_t scratch_ints = 0;
     double last_S = 0.0;
+    long long pend_i0 = 0, pend_i1 = 0;
+    bool interior_pending = false;
 
     ~Solver() override {
         cudaSetDevice(d.device);
@@ -471,13 +474,26 @@ struct Solver final : SolverBase {
             CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
             launches++;
         }
-        if ((r = launch_range(i0, i1, mom, res, d_acc))) return r;
+        pend_i0 = i0, pend_i1 = i1, interior_pending = true;
         in_step = true;
         return 0;
+    }
+    // the interior planes: queued AFTER the caller posted the halo transfers, so that the
+    // transfer (on the transport's stream) overlaps this launch
+    int step_interior() override {
+        if (!in_step) FAIL(LBM_ERR_STATE, "lbm_step_interior without lbm_step_begin");
+        if (!interior_pending) return 0;
+        CK(cudaSetDevice(d.device));
+        interior_pending = false;
+        return launch_range(pend_i0, pend_i1, step_flags & LBM_STEP_MOMENTS, step_flags & LBM_STEP_VELSUM, d_acc);
     }
     int step_end() override {
         if (!in_step) FAIL(LBM_ERR_STATE, "lbm_step_end without lbm_step_begin");
         CK(cudaSetDevice(d.device));
+        if (interior_pending) {
+            int r = step_interior();
+            if (r) return r;
+        }
         if (lo_halo) {
             CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
             launches++;
@@ -973,6 +989,7 @@ int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_
     return h->s->halo_buffers(side, send, recv, bytes);
 }
 int lbm_step_begin(lbm_handle h, int32_t flags) { H_OR_FAIL; return h->s->step_begin(flags); }
+int lbm_step_interior(lbm_handle h) { H_OR_FAIL; return h->s->step_interior(); }
 int lbm_step_end(lbm_handle h) { H_OR_FAIL; return h->s->step_end(); }
 int lbm_last_velsum(lbm_handle h, double *v) { H_OR_FAIL; return v ? h->s->last_velsum(v) : LBM_ERR_ARG; }
 void *lbm_stream(lbm_handle h) { return h ? h->s->stream_ptr() : nullptr; }

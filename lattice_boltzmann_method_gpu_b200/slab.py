@@ -1,0 +1,150 @@
+"""z-slab domain decomposition over the GPUs of one box.
+
+The reference is single-GPU; this is new work whose oracle is "N slabs == one domain, bit for bit".
+One process per GPU (torchrun); rank r owns global planes [z_begin, z_end) plus one halo plane per
+interior face.  Per time step each rank sends, per face, the 5 populations that cross it
+(c_z = +1: q in {5,11,13,15,16} upward, c_z = -1: q in {6,12,14,17,18} downward) of its outermost
+owned plane -- one contiguous staging buffer per face, packed by the library right after the face
+planes were computed so the transfer overlaps the interior update -- with
+torch.distributed P2P ops (NCCL over NVLink on GPUs; gloo on CPU for the host-logic tests).
+
+Nothing here computes: the kernels live in liblbm_b200.so.  `exchange_halos` and `slab_ranges` /
+`compact_offsets` are backend-agnostic so the same code runs under gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+
+def slab_ranges(nz: int, world: int):
+    """contiguous, near-equal z ranges; every slab gets at least one plane"""
+    if world > nz:
+        raise ValueError("more slabs than planes")
+    base, rem = divmod(nz, world)
+    out, z = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+def compact_offsets(local_counts):
+    """exclusive running sum of the per-slab stored-node counts: the single-domain z,y,x numbering
+    of index_transform (bifurcation.cu:241-252) continues across slabs"""
+    offs, run = [], 0
+    for c in local_counts:
+        offs.append(run)
+        run += int(c)
+    return offs, run
+
+
+def exchange_halos(send_lo, recv_lo, send_hi, recv_hi, rank: int, world: int, group=None):
+    """Post the (up to four) point-to-point transfers of one step and return the work handles.
+
+    send_lo -> rank-1's recv_hi,  send_hi -> rank+1's recv_lo.  Any of the tensors may be None at
+    the outer faces of the domain.  Works for CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch.distributed as dist
+
+    ops = []
+    if rank > 0 and send_lo is not None:
+        ops.append(dist.P2POp(dist.isend, send_lo, rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_lo, rank - 1, group))
+    if rank < world - 1 and send_hi is not None:
+        ops.append(dist.P2POp(dist.isend, send_hi, rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, recv_hi, rank + 1, group))
+    if not ops:
+        return []
+    return dist.batch_isend_irecv(ops)
+
+
+class _DevBuf:
+    """zero-copy view of a library-owned device buffer for torch (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, nbytes: int, dtype: np.dtype):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes // dtype.itemsize,), "typestr": dtype.str, "data": (ptr, False), "version": 2,
+            "strides": None,
+        }
+
+
+class SlabCase(api.Case):
+    """A `Case` that owns one z-slab of a larger domain and steps in lock-step with its neighbours."""
+
+    def __init__(self, desc: api.CaseDesc, group=None):
+        import torch.distributed as dist
+
+        super().__init__(desc)
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._bufs = None
+
+    def setup(self, flag=None, bc_planes=None):
+        """geo_pre -> (all-gather of stored counts) -> index_transform -> read_vel -> initialize"""
+        import torch
+        import torch.distributed as dist
+
+        if flag is not None:
+            self.set_flag(flag)
+        self.geo_pre()
+        mine = torch.tensor([self.local_stored_count()], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine, group=self.group)
+        offs, total = compact_offsets([int(t.item()) for t in allc])
+        self.set_compact_offset(offs[self.rank], total)
+        self.index_transform()
+        if bc_planes is not None:
+            self.set_bc_planes(*bc_planes)
+        self.initialize()
+        self._wrap_buffers()
+
+    def _wrap_buffers(self):
+        import torch
+
+        self._ext = torch.cuda.ExternalStream(self.stream)
+        bufs = []
+        for side in (0, 1):
+            s, r, n = self.halo_buffers(side)
+            if n == 0:
+                bufs.append((None, None))
+            else:
+                bufs.append((torch.as_tensor(_DevBuf(s, n, self.dtype), device="cuda"),
+                             torch.as_tensor(_DevBuf(r, n, self.dtype), device="cuda")))
+        self._bufs = bufs
+
+    def _one_step(self, flags=0):
+        import torch
+
+        self.step_begin(flags)  # face planes + pack, queued on the library's stream
+        (s_lo, r_lo), (s_hi, r_hi) = self._bufs
+        # torch.distributed orders NCCL's stream after what `self._ext` holds so far (faces + pack)
+        with torch.cuda.stream(self._ext):
+            works = exchange_halos(s_lo, r_lo, s_hi, r_hi, self.rank, self.world, self.group)
+        self.step_interior()  # interior planes run while the faces travel over NVLink
+        with torch.cuda.stream(self._ext):
+            for w in works:
+                w.wait()  # stream-ordered wait, no host sync
+        self.step_end()  # unpack + buffer swap
+
+    def step(self, n: int = 1):
+        for i in range(int(n)):
+            self._one_step(api.STEP_MOMENTS if i == n - 1 else 0)
+        self.sync()
+
+    def step_timed(self, n: int) -> float:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self._ext):
+            e0.record()
+        for i in range(int(n)):
+            self._one_step(api.STEP_MOMENTS if i == n - 1 else 0)
+        with torch.cuda.stream(self._ext):
+            e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)

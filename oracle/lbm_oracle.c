@@ -308,6 +308,10 @@ typedef struct {
     REAL cor_uin, cor_uout, cor_usub;
     double pulse_amp, pulse_period; /* extension: u_in(t) = u_in * (1 + A sin(2 pi t / T)) */
     long step_count;
+    int nfl;         /* fluid nodes */
+    int32_t *flist;  /* their compact ids, ascending */
+    int32_t *pull;   /* [19][nfl] compact id of the pull source x - c_q (or -1): the index
+                        lookups of bif:445-571 hoisted out of the time loop */
     int nb;          /* boundary (label 1,2,3,5,6,7 / ldc 1,2) nodes */
     int32_t *blist;  /* their compact ids */
     REAL *bscratch;  /* 19*nb snapshot outputs */
@@ -443,12 +447,28 @@ FN(orc_state) *FN(orc_create)(int case_id, int nx, int ny, int nz, const int32_t
     s->uz = (REAL *)calloc(nlat, sizeof(REAL));
     s->inlety = (REAL *)calloc((size_t)nx * nz, sizeof(REAL));
     s->outlety = (REAL *)calloc((size_t)nx * nz, sizeof(REAL));
+    s->nfl = 0;
+    for (int i = 0; i < nlat; i++) s->nfl += geo[s->cart[i]] == s->fluid_label;
+    s->flist = (int32_t *)malloc((size_t)(s->nfl ? s->nfl : 1) * sizeof(int32_t));
+    s->pull = (int32_t *)malloc((size_t)19 * (s->nfl ? s->nfl : 1) * sizeof(int32_t));
+    k = 0;
+    for (int i = 0; i < nlat; i++)
+        if (geo[s->cart[i]] == s->fluid_label) s->flist[k++] = i;
+    for (int j = 0; j < s->nfl; j++) {
+        size_t c = (size_t)s->cart[s->flist[j]];
+        int x = (int)(c % nx), y = (int)((c / nx) % ny), z = (int)(c / ((size_t)nx * ny));
+        for (int q = 0; q < 19; q++) {
+            int xx = x - CX[q], yy = y - CY[q], zz = z - CZ[q];
+            int ok = xx >= 0 && xx < nx && yy >= 0 && yy < ny && zz >= 0 && zz < nz;
+            s->pull[(size_t)q * s->nfl + j] = ok ? index[(size_t)xx + (size_t)nx * ((size_t)yy + (size_t)ny * zz)] : -1;
+        }
+    }
     return s;
 }
 
 void FN(orc_destroy)(FN(orc_state) *s) {
     if (!s) return;
-    free(s->geo), free(s->index), free(s->cart), free(s->blist), free(s->bscratch);
+    free(s->geo), free(s->index), free(s->cart), free(s->blist), free(s->bscratch), free(s->flist), free(s->pull);
     free(s->src), free(s->dst), free(s->rho), free(s->ux), free(s->uy), free(s->uz);
     free(s->inlety), free(s->outlety);
     free(s);
@@ -554,16 +574,14 @@ static void wall_gather(const FN(orc_state) *s, const REAL *buf, int x, int y, i
 
 /* fluid branch of `update`: ldc:204-369, pos:405-582, bif:445-635 */
 static void update_fluid(FN(orc_state) *s) {
-    const int nlat = s->nlat;
+    const int nlat = s->nlat, nfl = s->nfl;
     const REAL tau = s->tau;
 #pragma omp parallel for schedule(static)
-    for (int i = 0; i < nlat; i++) {
-        size_t c = (size_t)s->cart[i];
-        if (s->geo[c] != s->fluid_label) continue;
-        int x = (int)(c % s->nx), y = (int)((c / s->nx) % s->ny), z = (int)(c / ((size_t)s->nx * s->ny));
+    for (int j = 0; j < nfl; j++) {
+        const int i = s->flist[j];
         REAL f[19], feq[19];
         for (int q = 0; q < 19; q++) {
-            int n = nb_idx(s, x, y, z, -CX[q], -CY[q], -CZ[q], 0);
+            int n = s->pull[(size_t)q * nfl + j];
             f[q] = n >= 0 ? s->src[(size_t)q * nlat + n] : R(0.0);
         }
         REAL rho = R(0.0);

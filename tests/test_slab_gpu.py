@@ -1,0 +1,108 @@
+"""GPU: z-slab decomposition.  The reference is single-GPU, so the oracle of the multi-GPU path is
+"P slabs == one domain, bit for bit".  Here the P slabs live on ONE device ("virtual slabs"): the
+same halo pack / unpack / face-first code path as the multi-GPU run, with the transfer done by a
+device-to-device copy instead of NCCL."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def run_slabs(name, n, P, steps, precision, math_mode, pulse=None):
+    import torch
+
+    import lattice_boltzmann_method_gpu_b200 as L
+    from lattice_boltzmann_method_gpu_b200 import slab
+
+    nz = {"ldc": n, "pos": n, "bif": 32, "cor": 44}[name]
+    ranges = slab.slab_ranges(nz, P)
+    cs = [H.gpu_case(name, n, precision, math_mode, pulse=pulse, z_range=r) for r in ranges]
+    for c in cs:
+        c.geo_pre()
+    offs, total = slab.compact_offsets([c.local_stored_count() for c in cs])
+    for c, o in zip(cs, offs):
+        c.set_compact_offset(o, total)
+        assert c.index_transform() == total
+        if name == "bif":
+            c.set_bc_planes(*H.bif_bc_planes())
+        c.initialize()
+
+    def view(c, side):
+        s, r, nbytes = c.halo_buffers(side)
+        if nbytes == 0:
+            return None, None
+        mk = lambda p: torch.as_tensor(slab._DevBuf(p, nbytes, c.dtype), device="cuda")
+        return mk(s), mk(r)
+
+    bufs = [(view(c, 0), view(c, 1)) for c in cs]
+    for it in range(steps):
+        flags = L.STEP_MOMENTS if it == steps - 1 else 0
+        for c in cs:
+            c.step_begin(flags)
+        for c in cs:
+            c.step_interior()
+            c.sync()
+        for r in range(P - 1):
+            (_, _), (s_hi, r_hi) = bufs[r]
+            (s_lo, r_lo), _ = bufs[r + 1]
+            r_lo.copy_(s_hi)  # upward-moving populations of slab r's top plane
+            r_hi.copy_(s_lo)  # downward-moving populations of slab r+1's bottom plane
+        torch.cuda.synchronize()
+        for c in cs:
+            c.step_end()
+    for c in cs:
+        c.sync()
+    return cs, total
+
+
+@pytest.mark.parametrize("name,n,P", [("ldc", 24, 3), ("ldc", 20, 5), ("pos", 24, 2), ("bif", None, 4), ("cor", None, 3)])
+@pytest.mark.parametrize("math_name", ["strict", "fast"])
+def test_slabs_equal_single_domain_bitwise(name, n, P, math_name):
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    mm = L.MATH_STRICT if math_name == "strict" else L.MATH_FAST
+    steps = 23
+    one = H.gpu_case(name, n, L.F64, mm)
+    nlat = H.gpu_setup(one, name)
+    one.step(steps)
+    ref = one.get_fields()
+    cs, total = run_slabs(name, n, P, steps, L.F64, mm)
+    assert total == nlat
+    assert np.array_equal(np.concatenate([c.get_geo() for c in cs]), one.get_geo())
+    assert np.array_equal(np.concatenate([c.get_index() for c in cs]), one.get_index())
+    assert sum(c.num_fluid for c in cs) == one.num_fluid
+    parts = [c.get_fields() for c in cs]
+    firsts = [c.compact_first for c in cs]
+    assert firsts == sorted(firsts) and firsts[0] == 0
+    for k in range(4):
+        got = np.concatenate([p[k] for p in parts])
+        assert np.array_equal(got, ref[k]), f"field {k}: max diff {np.abs(got - ref[k]).max()}"
+
+
+def test_one_plane_slabs():
+    """degenerate decomposition: every interior slab owns a single plane (top face == bottom face)"""
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    n, steps = 12, 9
+    one = H.gpu_case("ldc", n, L.F32, L.MATH_FAST)
+    H.gpu_setup(one, "ldc")
+    one.step(steps)
+    ref = one.get_fields()
+    cs, _ = run_slabs("ldc", n, n, steps, L.F32, L.MATH_FAST)
+    for k in range(4):
+        assert np.array_equal(np.concatenate([c.get_fields()[k] for c in cs]), ref[k])
+
+
+def test_pulsatile_slabs():
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    pulse = (0.25, 30.0)
+    one = H.gpu_case("bif", None, L.F64, L.MATH_FAST, pulse=pulse)
+    H.gpu_setup(one, "bif")
+    one.step(40)
+    ref = one.get_fields()
+    cs, _ = run_slabs("bif", None, 2, 40, L.F64, L.MATH_FAST, pulse=pulse)
+    for k in range(4):
+        assert np.array_equal(np.concatenate([c.get_fields()[k] for c in cs]), ref[k])
