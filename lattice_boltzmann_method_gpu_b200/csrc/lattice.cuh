@@ -158,18 +158,25 @@ __device__ __forceinline__ void collide_bgk(T (&f)[Q], T tau, T inv_tau, T &rho,
         T mz = ((f[5] - f[6]) + (f[11] - f[14])) + ((f[13] - f[12]) + (f[15] - f[18])) + (f[16] - f[17]);
         rho = r;
         ux = mx * inv, uy = my * inv, uz = mz * inv;
-        const T om = inv_tau, om1 = T(1.0) - inv_tau;
-        // feq_q = rho w_q (1 + 3cu + 4.5cu^2 - 1.5u^2);  f* = (1-om) f + om feq
+        // f* = f + om (feq - f): the difference is formed first, like the reference's
+        // f - (f - feq)/tau, so the rounding error scales with the (small) non-equilibrium
+        // part.  The algebraically equal (1-om) f + om feq cancels two O(f) terms when
+        // tau < 1 and is 3-10x less accurate in fp32 (measured, profiles/r01_notes.md).
+        const T om = inv_tau;
+        // feq_q = rho w_q (1 + 3cu + 4.5cu^2 - 1.5u^2)
         const T base = T(1.0) - T(1.5) * (ux * ux + uy * uy + uz * uz);
-        const T k0 = om * r * T(1.0 / 3.0), k1 = om * r * T(1.0 / 18.0), k2 = om * r * T(1.0 / 36.0);
-        f[0] = om1 * f[0] + k0 * base;
+        // rho w_q by correctly rounded DIVISION, as the reference does (rho/3, rho/18, rho/36):
+        // multiplying by a rounded 1/18 gives every cell the same signed error in sum_q feq_q,
+        // i.e. a coherent mass drift of ~2 ulp per step -- visible in fp32 after 1000 steps
+        const T k0 = r / T(3.0), k1 = r / T(18.0), k2 = T(0.5) * k1;
+        f[0] = f[0] + om * (k0 * base - f[0]);
 #define LBM_PAIR(qp, qm, cu, kw)                                    \
     {                                                               \
         T cu_ = (cu);                                               \
         T even = base + T(4.5) * cu_ * cu_;                         \
         T odd = T(3.0) * cu_;                                       \
-        f[qp] = om1 * f[qp] + (kw) * (even + odd);                  \
-        f[qm] = om1 * f[qm] + (kw) * (even - odd);                  \
+        f[qp] = f[qp] + om * ((kw) * (even + odd) - f[qp]);         \
+        f[qm] = f[qm] + om * ((kw) * (even - odd) - f[qm]);         \
     }
         LBM_PAIR(1, 2, ux, k1)
         LBM_PAIR(3, 4, uy, k1)

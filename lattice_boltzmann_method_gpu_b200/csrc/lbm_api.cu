@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -373,7 +374,11 @@ struct Solver final : SolverBase {
         const long long cells = box.cells();
         qstride = cells + 64;  // de-phase the 19 streams a little; keeps 256-B alignment
         if (!d_fa) {
-            if (dalloc(&d_fa, (size_t)qstride * Q) || dalloc(&d_fb, (size_t)qstride * Q)) return LBM_ERR_NOMEM;
+            // tail guard: the speculative step form pulls for every cell, up to plane+px beyond the last one
+            const size_t fsize = (size_t)qstride * Q + (size_t)box.plane + box.px + 64;
+            if (dalloc(&d_fa, fsize) || dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
+            CK(cudaMemsetAsync(d_fa, 0, fsize * sizeof(T), st));
+            CK(cudaMemsetAsync(d_fb, 0, fsize * sizeof(T), st));
             if (dalloc(&d_rho, (size_t)cells) || dalloc(&d_ux, (size_t)cells) || dalloc(&d_uy, (size_t)cells) ||
                 dalloc(&d_uz, (size_t)cells))
                 return LBM_ERR_NOMEM;
@@ -413,6 +418,9 @@ struct Solver final : SolverBase {
         for (int i = 0; i < LBM_MAX_BC; i++) p.bc[i] = bc[i];
         p.plane_in = d_plane_in, p.plane_out = d_plane_out;
         p.parity = (int)(steps & 1);
+        // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
+        const char *force = getenv("LBM_SPECULATIVE");
+        p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
         return p;
     }
     int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc) {

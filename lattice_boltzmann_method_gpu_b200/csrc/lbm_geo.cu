@@ -278,13 +278,18 @@ __global__ void k_node_words(const int32_t *label, uint32_t *node, uint8_t *seg,
         label8[c] = (int8_t)g;
         if (p.x < b.nx && g == fluid_label && p.z >= own_z0 && p.z < own_z1) {
             w = 0;
+            bool walls_only = true;
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 int x = p.x - cxq(q), y = p.y - cyq(q), z = p.z - czq(q);
                 bool inb = x >= 0 && x < b.nx && y >= 0 && y < b.ny && z >= b.z0 && z < b.z1;
                 int gs = inb ? label[cell_of(b, x, y, z)] : 0;
-                if (gs != fluid_label) w |= (1u << q);
+                if (gs != fluid_label) {
+                    w |= (1u << q);
+                    if (gs != 1) walls_only = false;
+                }
             }
+            if (w && walls_only) w |= NODE_WALLS_ONLY;
         }
         node[c] = w;
     }

@@ -15,6 +15,9 @@ namespace lbm {
 constexpr int Q = 19;  // D3Q19
 constexpr uint32_t NODE_SKIP = 1u;
 constexpr uint32_t NODE_LINKS = 0x7FFFEu;
+//   bit 31       : every non-fluid source of this node is a wall (label 1): all its
+//                  links are plain half-way bounce-back, handled inline
+constexpr uint32_t NODE_WALLS_ONLY = 0x80000000u;
 
 // per 32-cell segment summary (one warp of the dense kernels)
 enum : uint8_t { SEG_BULK = 0, SEG_MIXED = 1, SEG_EMPTY = 2 };
@@ -59,6 +62,7 @@ struct StepParams {
     BcEntry bc[LBM_MAX_BC];
     const T *plane_in, *plane_out;  // nx * nz(global) each
     int parity;                     // AA: 0 even (local) step, 1 odd (shifted) step
+    int speculative;                // issue the population loads before the segment class is known
 };
 
 template <typename T>

@@ -27,8 +27,9 @@
 //
 // One warp = one 32-cell segment.  seg[] classifies segments: BULK (all 32 are
 // fluid with fluid sources only -> no node-word load, no divergence), MIXED, or
-// EMPTY (nothing to do -> the warp exits after one byte load).
+// EMPTY (nothing to do).
 #pragma once
+#include <cstdlib>
 #include "lattice.cuh"
 #include "lbm_internal.h"
 
@@ -69,9 +70,11 @@ __device__ __forceinline__ T feq_bc_axis(T rw, int cs, T u) {
     return rw * (T(1.0) - T(1.5) * u * u);
 }
 
-// Value this fluid node (cell c, moments rho/u, post-collision g_q and g_opp)
-// must leave in slot (q, s = c - off_q).  Returns false for a static link.
-// Rare path: kept out of line so the bulk path stays small.
+// Slow path of a boundary link (inlet / outlet / lid / static source): value this
+// fluid node (cell c, moments rho/u, post-collision g_q and g_opp) must leave in
+// slot (q, s = c - off_q); NaN-free sentinel `false` for a static link.  Only
+// nodes next to an inlet/outlet/lid get here -- wall-only nodes bounce back
+// inline -- so it is kept out of line and the bulk path stays small.
 template <typename T>
 __device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, int q, T rho, T ux, T uy, T uz, T gq,
                                            T gopp, T *out) {
@@ -101,47 +104,71 @@ __device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, 
     return true;
 }
 
-template <typename T>
-__device__ __forceinline__ void accumulate_velsum(double *acc, T ux, T uy, T uz, bool active) {
-    // |u| as the reference forms it (ldc.cu:464), summed in double: warp shuffle
-    // tree, then one atomic per warp
-    double v = active ? (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz)) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(acc, v);
-}
-
 // ---------------------------------------------------------------------------
 // two-buffer pull step
 // ---------------------------------------------------------------------------
-template <typename T, bool STRICT, bool MOMENTS, bool RESID>
-__global__ void __launch_bounds__(256) k_step_dense_ab(const __grid_constant__ StepParams<T> p) {
-    const long long c = p.c_begin + (long long)blockIdx.x * 256 + threadIdx.x;
-    if (c >= p.c_end) return;  // ranges are multiples of 32 cells: warp-uniform
-    const uint8_t kind = p.seg[c >> 5];
-    if (kind == SEG_EMPTY) return;
-    uint32_t node = 0;
-    if (kind != SEG_BULK) node = p.node[c];
-    const bool fluid = !(node & NODE_SKIP);
+// One warp per 32-cell segment, one CTA per B consecutive cells.  Two forms:
+//   SPEC = false : class byte -> (node word) -> 19 population loads.  Nothing is
+//                  read for EMPTY segments or non-fluid cells; the class byte
+//                  (L2-resident) sits on the critical path.
+//   SPEC = true  : the 19 population loads, the class byte and the node word are
+//                  all issued up front, for every thread; non-fluid threads drop
+//                  the values.  No dependent load precedes the DRAM reads.  Chosen
+//                  by the host when >= 90 % of the launched cells are fluid (dense
+//                  cavities), where the wasted reads are a few percent.
+// The kernel is latency-bound per warp, so resident warps matter more than
+// anything else: CTA shape and register cap are picked per precision
+// (fp64: 128 threads x 5 CTAs/SM, 96 registers; fp32: 128 x 8, 64 registers).
+// Measurements behind every choice here: profiles/r01_notes.md.
+__host__ __device__ constexpr int cfg_block(int cfg) {
+    constexpr int b[4] = {256, 256, 128, 128};
+    return b[cfg];
+}
+__host__ __device__ constexpr int cfg_minb(int cfg) {
+    constexpr int m[4] = {2, 3, 5, 8};
+    return m[cfg];
+}
+template <typename T>
+constexpr int default_cfg() {
+    return sizeof(T) == 8 ? 2 : 3;
+}
 
-    T rho = T(0), ux = T(0), uy = T(0), uz = T(0);
-    if (fluid) {
-        const Box &b = p.box;
-        const T *src = p.src + c;
-        T f[Q];
+__device__ __forceinline__ double ld_spec(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_spec(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// collide, store, moments, boundary links of one fluid cell whose post-streaming
+// populations are already in f[]
+template <typename T, bool STRICT, bool MOMENTS, bool RESID>
+__device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c, uint32_t node, T (&f)[Q], double &velsum) {
+    const Box &b = p.box;
+    T rho, ux, uy, uz;
+    collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+    T *dst = p.dst + c;
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-            f[q] = ld_stream(src + (long long)q * p.qstride - off);
-        }
-        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-        T *dst = p.dst + c;
+    for (int q = 0; q < Q; q++) dst[(long long)q * p.qstride] = f[q];
+    if (MOMENTS) {
+        p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
+    }
+    if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
+    if (node & NODE_LINKS) {
+        if (node & NODE_WALLS_ONLY) {
+            // half-way bounce-back, inline: slot (q, x - c_q) <- g_opp(q)(x)   (bif:781-798)
 #pragma unroll
-        for (int q = 0; q < Q; q++) dst[(long long)q * p.qstride] = f[q];
-        if (MOMENTS) {
-            p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
-        }
-        if (node & NODE_LINKS) {
+            for (int q = 1; q < Q; q++) {
+                if (node & (1u << q)) {
+                    const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+                    dst[(long long)q * p.qstride - off] = f[oppq(q)];
+                }
+            }
+        } else {
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 if (node & (1u << q)) {
@@ -154,20 +181,67 @@ __global__ void __launch_bounds__(256) k_step_dense_ab(const __grid_constant__ S
             }
         }
     }
-    if (RESID) accumulate_velsum<T>(p.resid, ux, uy, uz, fluid);
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool SPEC, int CFG>
+__global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense_ab(const __grid_constant__ StepParams<T> p) {
+    const Box &b = p.box;
+    const long long c = p.c_begin + (long long)blockIdx.x * cfg_block(CFG) + threadIdx.x;
+    if (c >= p.c_end) return;  // ranges are whole planes (multiples of 32 cells): warp-uniform
+    const T *src = p.src + c;
+    T f[Q];
+    uint32_t node;
+    const uint32_t kind = p.seg[c >> 5];
+    if (SPEC) {
+        // every thread pulls; the buffers carry a tail guard so all addresses are mapped
+        node = p.node[c];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+            f[q] = ld_spec(src + (long long)q * p.qstride - off);
+        }
+        if (kind == SEG_EMPTY) return;
+    } else {
+        if (kind == SEG_EMPTY) return;
+        node = kind == SEG_MIXED ? p.node[c] : 0u;
+    }
+    double velsum = 0.0;
+    if (!(node & NODE_SKIP)) {
+        if (!SPEC) {
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+                f[q] = ld_stream(src + (long long)q * p.qstride - off);
+            }
+        }
+        finish_cell<T, STRICT, MOMENTS, RESID>(p, c, node, f, velsum);
+    }
+    if (RESID) {
+        // warp shuffle tree, then one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
+        if ((threadIdx.x & 31) == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    }
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, int CFG>
+cudaError_t launch_cfg(const StepParams<T> &p, cudaStream_t s) {
+    constexpr int B = cfg_block(CFG);
+    const unsigned nb = (unsigned)((p.c_end - p.c_begin + B - 1) / B);
+    if (p.speculative) k_step_dense_ab<T, STRICT, MOMENTS, RESID, true, CFG><<<nb, B, 0, s>>>(p);
+    else k_step_dense_ab<T, STRICT, MOMENTS, RESID, false, CFG><<<nb, B, 0, s>>>(p);
+    return cudaGetLastError();
 }
 
 template <typename T, bool STRICT>
 cudaError_t launch_step_dense_impl(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s) {
-    const long long n = p.c_end - p.c_begin;
-    if (n <= 0) return cudaSuccess;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (p.c_end <= p.c_begin) return cudaSuccess;
     (void)storage;
-    if (moments && resid) k_step_dense_ab<T, STRICT, true, true><<<blocks, 256, 0, s>>>(p);
-    else if (moments) k_step_dense_ab<T, STRICT, true, false><<<blocks, 256, 0, s>>>(p);
-    else if (resid) k_step_dense_ab<T, STRICT, false, true><<<blocks, 256, 0, s>>>(p);
-    else k_step_dense_ab<T, STRICT, false, false><<<blocks, 256, 0, s>>>(p);
-    return cudaGetLastError();
+    constexpr int C = default_cfg<T>();
+    if (moments && resid) return launch_cfg<T, STRICT, true, true, C>(p, s);
+    if (moments) return launch_cfg<T, STRICT, true, false, C>(p, s);
+    if (resid) return launch_cfg<T, STRICT, false, true, C>(p, s);
+    return launch_cfg<T, STRICT, false, false, C>(p, s);
 }
 
 }  // namespace lbm

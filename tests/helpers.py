@@ -50,7 +50,10 @@ def synthetic_openings_mask(nx=40, ny=36, nz=44):
     return flag, rules
 
 
-COR_SPEEDS = dict(uin=0.02, uout=0.012, usub=0.004)
+# the reference's own lattice speeds (cor.cu:302-306): 0.1745, 0.1, 0.02 m/s over C_U = 2.74909
+COR_SPEEDS = dict(uin=float(np.float32(0.1745) / np.float32(2.74909090909091)),
+                  uout=float(np.float32(0.1) / np.float32(2.74909090909091)),
+                  usub=float(np.float32(0.02) / np.float32(2.74909090909091)))
 
 
 def oracle_case(name, n=None, dtype=np.float32, pulse=None, shipped_bc=False):

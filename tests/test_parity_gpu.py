@@ -72,9 +72,13 @@ def test_strict_populations_bit_exact(name, n):
         assert np.array_equal(fo[q, src], fg[q, src]), f"direction {q}"
 
 
-@pytest.mark.parametrize("name,n,steps", [("ldc", 32, 400), ("pos", 24, 400), ("bif", None, 400), ("cor", None, 300)])
-@pytest.mark.parametrize("prec,tol", [("f32", 1e-5), ("f64", 1e-12)])
-def test_fast_fields_within_tolerance(name, n, steps, prec, tol):
+@pytest.mark.parametrize("name,n", [("ldc", 32), ("pos", 24), ("bif", None), ("cor", None)])
+@pytest.mark.parametrize("prec,tol,steps", [("f32", 1e-5, 100), ("f64", 1e-12, 400)])
+def test_fast_fields_within_tolerance(name, n, prec, tol, steps):
+    """FAST (FMA-contracted, reciprocal-multiply) arithmetic vs the oracle's literal arithmetic:
+    1e-12 in fp64 after 400 steps, 1e-5 in fp32 after 100 steps (two fp32 evaluation orders drift
+    apart by the rounding noise of fp32 itself; test_fast_fp32_is_as_accurate_as_the_reference_order
+    bounds that drift against an fp64 run for longer horizons)."""
     lib = L()
     dt = np.float32 if prec == "f32" else np.float64
     o, geo, idx, nlat = H.oracle_case(name, n, dt)
@@ -86,6 +90,23 @@ def test_fast_fields_within_tolerance(name, n, steps, prec, tol):
     assert err <= tol, f"{name} {prec}: rel err {err:.3e} > {tol}"
 
 
+@pytest.mark.parametrize("name,n", [("ldc", 32), ("bif", None)])
+def test_fast_fp32_is_as_accurate_as_the_reference_order(name, n):
+    """after 1000 steps the FAST fp32 kernel is no further from an fp64 solution than the
+    reference's own fp32 evaluation order (the oracle in float) is"""
+    lib = L()
+    steps = 1000
+    o64, *_ = H.oracle_case(name, n, np.float64)
+    o32, *_ = H.oracle_case(name, n, np.float32)
+    c = H.gpu_case(name, n, lib.F32, lib.MATH_FAST)
+    H.gpu_setup(c, name)
+    o64.step(steps), o32.step(steps), c.step(steps)
+    truth = o64.fields()
+    e_ref = H.rel_err(o32.fields(), truth)
+    e_fast = H.rel_err(c.get_fields(), truth)
+    assert e_fast <= 2.0 * e_ref + 1e-7, (e_fast, e_ref)
+
+
 def test_shipped_bc_gives_rest_state():
     # code + data as shipped: inlet plane is all zero -> fluid stays at rest (SURVEY 8a5)
     lib = L()
@@ -93,7 +114,13 @@ def test_shipped_bc_gives_rest_state():
     H.gpu_setup(c, "bif", shipped_bc=True)
     c.step(25)
     rho, ux, uy, uz = c.get_fields()
-    assert not ux.any() and not uy.any() and not uz.any()
+    # "rest" up to fp32 rounding of the pressure outlet: the reference program itself ends at
+    # max|u| ~ 4e-6 after 4400 steps (gpurun capture of oracle/_ref/bif_ref, tools/capture_reference.py)
+    assert max(np.abs(ux).max(), np.abs(uy).max(), np.abs(uz).max()) < 1e-5
+    o, *_ = H.oracle_case("bif", None, np.float32, shipped_bc=True)
+    o.step(25)
+    for r, g in zip(o.fields(), (rho, ux, uy, uz)):
+        assert np.array_equal(r, g)
 
 
 @pytest.mark.parametrize("name", ["bif", "cor"])
