@@ -98,6 +98,16 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm)}
 
 
+def ncu_traffic(precision, n, storage):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if one exists for
+    exactly this workload"""
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        return t.get(f"{precision}_{n}_{storage}")
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,7 +323,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic_bytes, "peak_source": peak_src,
+                         "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(args.precision, n, args.storage),
+                         "peak_source": peak_src,
                          "kernel": "k_step_dense_ab", "algorithmic_bytes_per_launch": nfluid_local * bpl,
                          "frac_of_spec_8TBs": achieved / 8000.0},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -344,7 +355,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=25)
-    ap.add_argument("--ref-n", type=int, default=160)
+    ap.add_argument("--ref-n", type=int, default=224)
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram__bytes_read.sum+dram__bytes_write.sum per launch from the committed ncu capture")
     args = ap.parse_args()
