@@ -325,7 +325,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(args.precision, n, args.storage),
                          "peak_source": peak_src,
-                         "kernel": "k_step_dense_ab", "algorithmic_bytes_per_launch": nfluid_local * bpl,
+                         "kernel": "k_step_dense", "algorithmic_bytes_per_launch": nfluid_local * bpl,
                          "frac_of_spec_8TBs": achieved / 8000.0},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_ms_per_step": wall / args.steps * 1e3, "fluid_nodes": int(nfluid),

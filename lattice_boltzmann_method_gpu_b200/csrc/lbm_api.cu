@@ -123,7 +123,7 @@ struct Solver final : SolverBase {
             if (p) cudaFree(p);
         };
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
-        fr(d_fa), fr(d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
+        fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -360,7 +360,10 @@ struct Solver final : SolverBase {
     int initialize() override {
         if (!have_index) FAIL(LBM_ERR_STATE, "initialize before index_transform");
         CK(cudaSetDevice(d.device));
-        if (d.storage != LBM_STORE_DENSE_AB) FAIL(LBM_ERR_ARG, "storage %d not available in this build", d.storage);
+        if (d.storage != LBM_STORE_DENSE_AB && d.storage != LBM_STORE_DENSE_AA)
+            FAIL(LBM_ERR_ARG, "storage %d not available in this build", d.storage);
+        const bool aa = d.storage == LBM_STORE_DENSE_AA;
+        if (aa && (lo_halo || hi_halo)) FAIL(LBM_ERR_ARG, "in-place (AA) storage is single-domain only in this build");
         if (d.case_rule == LBM_CASE_GEO_Y_INOUT && !have_planes) {
             h_in.assign((size_t)d.nx * d.nz, 0.f), h_out = h_in;
             int r = upload_planes();
@@ -376,9 +379,14 @@ struct Solver final : SolverBase {
         if (!d_fa) {
             // tail guard: the speculative step form pulls for every cell, up to plane+px beyond the last one
             const size_t fsize = (size_t)qstride * Q + (size_t)box.plane + box.px + 64;
-            if (dalloc(&d_fa, fsize) || dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
+            if (dalloc(&d_fa, fsize)) return LBM_ERR_NOMEM;
             CK(cudaMemsetAsync(d_fa, 0, fsize * sizeof(T), st));
-            CK(cudaMemsetAsync(d_fb, 0, fsize * sizeof(T), st));
+            if (aa) {
+                d_fb = d_fa;  // one buffer, streamed in place
+            } else {
+                if (dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
+                CK(cudaMemsetAsync(d_fb, 0, fsize * sizeof(T), st));
+            }
             if (dalloc(&d_rho, (size_t)cells) || dalloc(&d_ux, (size_t)cells) || dalloc(&d_uy, (size_t)cells) ||
                 dalloc(&d_uz, (size_t)cells))
                 return LBM_ERR_NOMEM;
@@ -387,7 +395,7 @@ struct Solver final : SolverBase {
                     return LBM_ERR_NOMEM;
         }
         InitParams<T> ip{};
-        ip.fa = d_fa, ip.fb = d_fb, ip.qstride = qstride, ip.label = d_label;
+        ip.fa = d_fa, ip.fb = d_fb, ip.aa = aa ? 1 : 0, ip.qstride = qstride, ip.label = d_label;
         ip.rho = d_rho, ip.ux = d_ux, ip.uy = d_uy, ip.uz = d_uz;
         ip.box = box, ip.case_rule = d.case_rule, ip.u_max = (T)d.u_max;
         for (int i = 0; i < LBM_MAX_BC; i++) ip.bc[i] = bc[i];
@@ -418,6 +426,8 @@ struct Solver final : SolverBase {
         for (int i = 0; i < LBM_MAX_BC; i++) p.bc[i] = bc[i];
         p.plane_in = d_plane_in, p.plane_out = d_plane_out;
         p.parity = (int)(steps & 1);
+        p.case_rule = d.case_rule;
+        p.u_init = (T)d.u_max;
         // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
         const char *force = getenv("LBM_SPECULATIVE");
         p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
@@ -589,8 +599,9 @@ struct Solver final : SolverBase {
         const size_t n = (size_t)stored_own;
         T *tmp = nullptr;
         CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * Q * sizeof(T)));
+        const int layout = d.storage == LBM_STORE_DENSE_AA ? ((steps & 1) ? 2 : 1) : 0;
         cudaError_t e = launch_gather_pops<T>(d_cur, qstride, d_index, box, own_z0, own_z1, compact_first, (long long)n,
-                                              tmp, st);
+                                              layout, tmp, st);
         launches++;
         if (e == cudaSuccess) e = cudaMemcpyAsync(f, tmp, n * Q * sizeof(T), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

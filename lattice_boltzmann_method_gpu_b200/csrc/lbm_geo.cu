@@ -11,6 +11,7 @@
 // reference's literal expression order so that STRICT runs start bit-identical.
 #include "lattice.cuh"
 #include "lbm_internal.h"
+#include "init_rule.cuh"
 
 namespace lbm {
 
@@ -303,50 +304,41 @@ __global__ void k_node_words(const int32_t *label, uint32_t *node, uint8_t *seg,
 }
 
 // ---------------------------------------------------------------- initialize
-template <typename T>
-__device__ inline T parabola_at(const Box &b, T umax, int x, int z) {
-    T cx = T(b.nx - 1) / T(2.0), cz = T(b.nz - 1) / T(2.0), r = T(b.nx - 1) / T(2.0);
-    T dx = T(x) - cx, dz = T(z) - cz;
-    return umax * (T(1.0) - (dx * dx + dz * dz) / (r * r));
-}
-
 // rho = 1, u = 0 on every cell; boundary planes / labels get their initial
 // velocity; f = feq(rho,u) into both buffers (ldc.cu:504-580, pos:273-382,
 // bif:329-427, cor:277-350).  Cells the reference does not store (label 0,
 // padding) are given the rest state, the value "static" links read.
+// In-place (AA) storage starts with an even, purely local step, so slot (q,c) is
+// seeded with the population that step would have pulled: feq_q of cell c - c_q.
 template <typename T>
 __global__ void k_init(const __grid_constant__ InitParams<T> p) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const Box &b = p.box;
     if (c >= b.cells()) return;
     Coord co = coord_of(b, c);
-    T rho = T(1.0), ux = T(0.0), uy = T(0.0), uz = T(0.0);
-    const int g = p.label[c];
-    const bool inbox = co.x < b.nx;
-    if (inbox) {
-        if (p.case_rule == LBM_CASE_LDC) {
-            if (co.y == b.ny - 1 || co.y == b.ny - 2) uz = p.u_max;  // ldc.cu:523-531
-        } else if (p.case_rule == LBM_CASE_POISEUILLE) {
-            if (g != 0 && (co.y <= 1 || co.y >= b.ny - 2)) uy = parabola_at<T>(b, p.u_max, co.x, co.z);  // pos:295-341
-        } else if (p.case_rule == LBM_CASE_GEO_Y_INOUT) {
-            if (g != 0 && co.y == 1) uy = p.plane_in[co.x + (long long)co.z * b.nx];  // bif:349-373
-            if (g != 0 && co.y == b.ny - 2) uy = p.plane_out[co.x + (long long)co.z * b.nx];
-        } else {
-            if (g >= 2 && g < LBM_MAX_BC && g != 4 && p.bc[g].kind != LBM_BC_NONE) {  // cor:302-306
-                T v = (T)p.bc[g].init_value;
-                if (p.bc[g].vaxis == 0) ux = v;
-                else if (p.bc[g].vaxis == 1) uy = v;
-                else uz = v;
-            }
-        }
-    }
     T feq[Q];
-    if (p.case_rule == LBM_CASE_LDC) {
-        feq_all_ldc_init<T>(rho, ux, uy, uz, feq);
-    } else {
-        const T r3 = rho / T(3.0), r18 = rho / T(18.0), r36 = rho / T(36.0);
+    if (!p.aa) {
+        T ux, uy, uz;
+        const int g = co.x < b.nx ? p.label[c] : 0;
+        init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, g, co.x < b.nx ? co.x : -1, co.y, co.z,
+                         ux, uy, uz);
+        if (p.case_rule == LBM_CASE_LDC) {
+            feq_all_ldc_init<T>(T(1.0), ux, uy, uz, feq);
+        } else {
+            const T r3 = T(1.0) / T(3.0), r18 = T(1.0) / T(18.0), r36 = T(1.0) / T(36.0);
 #pragma unroll
-        for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+            for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int x = co.x - cxq(q), y = co.y - cyq(q), z = co.z - czq(q);
+            const bool in = co.x < b.nx && x >= 0 && x < b.nx && y >= 0 && y < b.ny && z >= b.z0 && z < b.z1;
+            const int g = in ? p.label[cell_of(b, x, y, z)] : 0;
+            T ux, uy, uz;
+            init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, g, in ? x : -1, y, z, ux, uy, uz);
+            feq[q] = init_feq_q<T>(p.case_rule, q, T(1.0), ux, uy, uz);
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
@@ -373,14 +365,23 @@ __global__ void k_gather_fields(const T *rho, const T *ux, const T *uy, const T 
     ouz[o] = fl ? uz[c] : T(0);
 }
 template <typename T>
-__global__ void k_gather_pops(const T *f, long long qstride, const int32_t *index, long long c0, long long c1,
-                              long long first, long long count, T *out) {
+__global__ void k_gather_pops(const T *f, long long qstride, const int32_t *index, Box b, long long c0, long long c1,
+                              long long first, long long count, int layout, T *out) {
     long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     int i = index[c];
     if (i < 0) return;
     long long o = (long long)i - first;
-    for (int q = 0; q < Q; q++) out[(long long)q * count + o] = f[(long long)q * qstride + c];
+    const long long cells = b.cells();
+    for (int q = 0; q < Q; q++) {
+        // "as if in d_scr after the swap": slot q of stored node y = what y + c_q pulls next
+        long long src;
+        if (layout == 0) src = (long long)q * qstride + c;
+        else if (layout == 1) src = (long long)q * qstride + c + ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
+        else src = (long long)oppq(q) * qstride + c;
+        const long long cell = src - (long long)(layout == 2 ? oppq(q) : q) * qstride;
+        out[(long long)q * count + o] = (cell >= 0 && cell < cells) ? f[src] : T(0);
+    }
 }
 
 // kind 0: sum sqrt(u^2) over every stored entry (non-fluid entries are 0)    ldc.cu:460-466,662
@@ -513,10 +514,10 @@ cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T
 }
 template <typename T>
 cudaError_t launch_gather_pops(const T *f, long long qstride, const int32_t *index, Box box, int own_z0, int own_z1,
-                               long long first, long long count, T *out, cudaStream_t s) {
+                               long long first, long long count, int layout, T *out, cudaStream_t s) {
     long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
     if (c1 <= c0) return cudaSuccess;
-    k_gather_pops<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(f, qstride, index, c0, c1, first, count, out);
+    k_gather_pops<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(f, qstride, index, box, c0, c1, first, count, layout, out);
     return cudaGetLastError();
 }
 template <typename T>
@@ -548,7 +549,7 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
                                                  const int32_t *, Box, int, int, int, long long, T *, T *, T *, T *,    \
                                                  cudaStream_t);                                                         \
     template cudaError_t launch_gather_pops<T>(const T *, long long, const int32_t *, Box, int, int, long long,         \
-                                               long long, T *, cudaStream_t);                                           \
+                                               long long, int, T *, cudaStream_t);                                           \
     template cudaError_t launch_reduce_fields<T>(const T *, const T *, const T *, const int32_t *, Box, int, int, int,  \
                                                  int, int, double *, cudaStream_t);                                     \
     template cudaError_t launch_halo_pack<T>(const T *, long long, Box, int, int, T *, cudaStream_t);                   \

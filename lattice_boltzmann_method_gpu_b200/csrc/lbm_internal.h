@@ -63,11 +63,14 @@ struct StepParams {
     const T *plane_in, *plane_out;  // nx * nz(global) each
     int parity;                     // AA: 0 even (local) step, 1 odd (shifted) step
     int speculative;                // issue the population loads before the segment class is known
+    int case_rule;                  // lbm_case_rule (initial-state rule, for static links in the AA odd step)
+    T u_init;                       // lbm_case_desc.u_max
 };
 
 template <typename T>
 struct InitParams {
-    T *fa, *fb;  // both buffers (fb may equal fa for in-place storage)
+    T *fa, *fb;  // both buffers (fb == fa for in-place storage)
+    int aa;      // in-place storage: slot (q,c) holds the PRE-STREAMED population feq_q(cell c - c_q)
     long long qstride;
     const int32_t *label;  // state box labels (int32)
     T *rho, *ux, *uy, *uz;
@@ -98,9 +101,10 @@ template <typename T>
 cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
                                  const int32_t *index, Box box, int own_z0, int own_z1, int fluid_label, long long first,
                                  T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s);
+// layout: 0 two-buffer (slot q of cell y), 1 AA before an even step (a[q][y+c_q]), 2 AA before an odd step (a[opp q][y])
 template <typename T>
 cudaError_t launch_gather_pops(const T *f, long long qstride, const int32_t *index, Box box, int own_z0, int own_z1,
-                               long long first, long long count, T *out, cudaStream_t s);
+                               long long first, long long count, int layout, T *out, cudaStream_t s);
 template <typename T>
 cudaError_t launch_reduce_fields(const T *ux, const T *uy, const T *uz, const int32_t *label, Box box, int own_z0,
                                  int own_z1, int kind, int fluid_label, int case_rule, double *out_dev, cudaStream_t s);

@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include "lattice.cuh"
 #include "lbm_internal.h"
+#include "init_rule.cuh"
 
 namespace lbm {
 
@@ -70,14 +71,30 @@ __device__ __forceinline__ T feq_bc_axis(T rw, int cs, T u) {
     return rw * (T(1.0) - T(1.5) * u * u);
 }
 
+// Storage modes of the populations
+//   MODE_AB      two buffers.  pull  src[q][c - off_q]         store dst[q][c]
+//                              boundary slot of link q:        dst[q][c - off_q]
+//   MODE_AA_EVEN one buffer, even step (purely local).
+//                              pull  a[q][c]                   store a[opp q][c]
+//                              boundary slot of link q:        a[opp q][c - off_q]   (read by the odd step)
+//   MODE_AA_ODD  one buffer, odd step.
+//                              pull  a[opp q][c - off_q]       store a[q][c + off_q] (only into fluid targets)
+//                              boundary slot of link q:        a[q][c]               (read by the even step)
+// AA-pattern streaming (Bailey et al. 2009) with the fluid-side boundaries of this file: every slot
+// a thread touches in a launch is touched by that thread only, so the update is in place.
+// The even step overwrites slot (q,c) of a link whose source is not fluid, therefore the ODD step
+// re-creates the constant of a static link there; in the other two modes static slots are simply
+// never written.
+enum { MODE_AB = 0, MODE_AA_EVEN = 1, MODE_AA_ODD = 2 };
+
 // Slow path of a boundary link (inlet / outlet / lid / static source): value this
 // fluid node (cell c, moments rho/u, post-collision g_q and g_opp) must leave in
-// slot (q, s = c - off_q); NaN-free sentinel `false` for a static link.  Only
-// nodes next to an inlet/outlet/lid get here -- wall-only nodes bounce back
-// inline -- so it is kept out of line and the bulk path stays small.
+// the link's slot; `false` when nothing is to be written (static link outside the
+// odd AA step).  Only nodes next to an inlet/outlet/lid get here -- wall-only nodes
+// bounce back inline -- so it is kept out of line and the bulk path stays small.
 template <typename T>
-__device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, int q, T rho, T ux, T uy, T uz, T gq,
-                                           T gopp, T *out) {
+__device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, int q, int mode, T rho, T ux, T uy, T uz,
+                                           T gq, T gopp, T *out) {
     const Box &b = p.box;
     const long long s = c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
     const int lab = p.label8[s];
@@ -85,9 +102,18 @@ __device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, 
         *out = gopp;
         return true;
     }
-    if (lab < 2 || lab >= LBM_MAX_BC) return false;
+    const bool bc_link = lab >= 2 && lab < LBM_MAX_BC && p.bc[lab].kind != LBM_BC_NONE &&
+                         caxis(q, p.bc[lab].naxis) == p.bc[lab].nsign;
+    const int sx = (int)(s % b.px), sy = (int)((s / b.px) % b.ny), sz = (int)(s / b.plane) + b.z0;
+    if (!bc_link) {
+        // static link: the initial population of s, feq_q(1, u0(s))
+        if (mode != MODE_AA_ODD) return false;
+        T u0x, u0y, u0z;
+        init_velocity<T>(p.case_rule, p.u_init, p.bc, p.plane_in, p.plane_out, b, lab, sx, sy, sz, u0x, u0y, u0z);
+        *out = init_feq_q<T>(p.case_rule, q, T(1.0), u0x, u0y, u0z);
+        return true;
+    }
     const BcEntry &e = p.bc[lab];
-    if (e.kind == LBM_BC_NONE || caxis(q, e.naxis) != e.nsign) return false;
     const T wden = q < 7 ? T(18.0) : T(36.0);
     const T feq = feq_lit<T>(q, rho / T(3.0), rho / T(18.0), rho / T(36.0), ux, uy, uz);
     T tmp;
@@ -95,7 +121,6 @@ __device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, 
         const T one = T(1.0);
         tmp = feq_lit<T>(q, one / T(3.0), one / T(18.0), one / T(36.0), ux, uy, uz);
     } else {
-        const int sx = (int)(s % b.px), sz = (int)(s / b.plane) + b.z0;
         const T u = bc_speed<T>(p, e, sx, sz);
         const T rw = e.kind == LBM_BC_V ? rho / wden : T(1.0) / wden;
         tmp = feq_bc_axis<T>(rw, caxis(q, e.vaxis), u);
@@ -105,7 +130,7 @@ __device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, 
 }
 
 // ---------------------------------------------------------------------------
-// two-buffer pull step
+// fused step
 // ---------------------------------------------------------------------------
 // One warp per 32-cell segment, one CTA per B consecutive cells.  Two forms:
 //   SPEC = false : class byte -> (node word) -> 19 population loads.  Nothing is
@@ -143,29 +168,67 @@ __device__ __forceinline__ float ld_spec(const float *p) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// in-place modes read and write the same array in one launch: no read-only (.nc) path there
+__device__ __forceinline__ double ld_spec_rw(const double *p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_spec_rw(const float *p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int MODE>
+__device__ __forceinline__ long long pull_index(int q, long long c, long long qs, long long off) {
+    if (MODE == MODE_AB) return (long long)q * qs + c - off;
+    if (MODE == MODE_AA_EVEN) return (long long)q * qs + c;
+    return (long long)oppq(q) * qs + c - off;
+}
+template <int MODE>
+__device__ __forceinline__ long long store_index(int q, long long c, long long qs, long long off) {
+    if (MODE == MODE_AB) return (long long)q * qs + c;
+    if (MODE == MODE_AA_EVEN) return (long long)oppq(q) * qs + c;
+    return (long long)q * qs + c + off;
+}
+template <int MODE>
+__device__ __forceinline__ long long slot_index(int q, long long c, long long qs, long long off) {
+    if (MODE == MODE_AB) return (long long)q * qs + c - off;
+    if (MODE == MODE_AA_EVEN) return (long long)oppq(q) * qs + c - off;
+    return (long long)q * qs + c;
+}
 
 // collide, store, moments, boundary links of one fluid cell whose post-streaming
 // populations are already in f[]
-template <typename T, bool STRICT, bool MOMENTS, bool RESID>
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, int MODE>
 __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c, uint32_t node, T (&f)[Q], double &velsum) {
     const Box &b = p.box;
     T rho, ux, uy, uz;
     collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-    T *dst = p.dst + c;
+    T *dst = p.dst;
 #pragma unroll
-    for (int q = 0; q < Q; q++) dst[(long long)q * p.qstride] = f[q];
+    for (int q = 0; q < Q; q++) {
+        const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+        if (MODE == MODE_AA_ODD) {
+            // push only into fluid targets: x + c_q is the source of link opp(q)
+            if (q == 0 || !(node & (1u << oppq(q)))) dst[store_index<MODE>(q, c, p.qstride, off)] = f[q];
+        } else {
+            dst[store_index<MODE>(q, c, p.qstride, off)] = f[q];
+        }
+    }
     if (MOMENTS) {
         p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
     }
     if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
     if (node & NODE_LINKS) {
         if (node & NODE_WALLS_ONLY) {
-            // half-way bounce-back, inline: slot (q, x - c_q) <- g_opp(q)(x)   (bif:781-798)
+            // half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 if (node & (1u << q)) {
                     const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                    dst[(long long)q * p.qstride - off] = f[oppq(q)];
+                    dst[slot_index<MODE>(q, c, p.qstride, off)] = f[oppq(q)];
                 }
             }
         } else {
@@ -173,9 +236,9 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
             for (int q = 1; q < Q; q++) {
                 if (node & (1u << q)) {
                     T h;
-                    if (boundary_link<T>(p, c, q, rho, ux, uy, uz, f[q], f[oppq(q)], &h)) {
+                    if (boundary_link<T>(p, c, q, MODE, rho, ux, uy, uz, f[q], f[oppq(q)], &h)) {
                         const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                        dst[(long long)q * p.qstride - off] = h;
+                        dst[slot_index<MODE>(q, c, p.qstride, off)] = h;
                     }
                 }
             }
@@ -183,22 +246,22 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
     }
 }
 
-template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool SPEC, int CFG>
-__global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense_ab(const __grid_constant__ StepParams<T> p) {
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool SPEC, int CFG, int MODE>
+__global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(const __grid_constant__ StepParams<T> p) {
     const Box &b = p.box;
     const long long c = p.c_begin + (long long)blockIdx.x * cfg_block(CFG) + threadIdx.x;
     if (c >= p.c_end) return;  // ranges are whole planes (multiples of 32 cells): warp-uniform
-    const T *src = p.src + c;
     T f[Q];
     uint32_t node;
     const uint32_t kind = p.seg[c >> 5];
     if (SPEC) {
-        // every thread pulls; the buffers carry a tail guard so all addresses are mapped
+        // every thread pulls; the buffers carry guards so all addresses are mapped
         node = p.node[c];
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-            f[q] = ld_spec(src + (long long)q * p.qstride - off);
+            const T *a = p.src + pull_index<MODE>(q, c, p.qstride, off);
+            f[q] = MODE == MODE_AB ? ld_spec(a) : ld_spec_rw(a);
         }
         if (kind == SEG_EMPTY) return;
     } else {
@@ -211,10 +274,11 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense_ab
 #pragma unroll
             for (int q = 0; q < Q; q++) {
                 const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                f[q] = ld_stream(src + (long long)q * p.qstride - off);
+                const T *a = p.src + pull_index<MODE>(q, c, p.qstride, off);
+                f[q] = MODE == MODE_AB ? ld_stream(a) : *a;
             }
         }
-        finish_cell<T, STRICT, MOMENTS, RESID>(p, c, node, f, velsum);
+        finish_cell<T, STRICT, MOMENTS, RESID, MODE>(p, c, node, f, velsum);
     }
     if (RESID) {
         // warp shuffle tree, then one atomic per warp
@@ -224,24 +288,32 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense_ab
     }
 }
 
-template <typename T, bool STRICT, bool MOMENTS, bool RESID, int CFG>
-cudaError_t launch_cfg(const StepParams<T> &p, cudaStream_t s) {
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, int CFG, int MODE>
+cudaError_t launch_mode(const StepParams<T> &p, cudaStream_t s) {
     constexpr int B = cfg_block(CFG);
     const unsigned nb = (unsigned)((p.c_end - p.c_begin + B - 1) / B);
-    if (p.speculative) k_step_dense_ab<T, STRICT, MOMENTS, RESID, true, CFG><<<nb, B, 0, s>>>(p);
-    else k_step_dense_ab<T, STRICT, MOMENTS, RESID, false, CFG><<<nb, B, 0, s>>>(p);
+    if (p.speculative) k_step_dense<T, STRICT, MOMENTS, RESID, true, CFG, MODE><<<nb, B, 0, s>>>(p);
+    else k_step_dense<T, STRICT, MOMENTS, RESID, false, CFG, MODE><<<nb, B, 0, s>>>(p);
     return cudaGetLastError();
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID>
+cudaError_t launch_cfg(const StepParams<T> &p, int storage, cudaStream_t s) {
+    constexpr int C = default_cfg<T>();
+    if (storage == LBM_STORE_DENSE_AA) {
+        if (p.parity == 0) return launch_mode<T, STRICT, MOMENTS, RESID, C, MODE_AA_EVEN>(p, s);
+        return launch_mode<T, STRICT, MOMENTS, RESID, C, MODE_AA_ODD>(p, s);
+    }
+    return launch_mode<T, STRICT, MOMENTS, RESID, C, MODE_AB>(p, s);
 }
 
 template <typename T, bool STRICT>
 cudaError_t launch_step_dense_impl(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s) {
     if (p.c_end <= p.c_begin) return cudaSuccess;
-    (void)storage;
-    constexpr int C = default_cfg<T>();
-    if (moments && resid) return launch_cfg<T, STRICT, true, true, C>(p, s);
-    if (moments) return launch_cfg<T, STRICT, true, false, C>(p, s);
-    if (resid) return launch_cfg<T, STRICT, false, true, C>(p, s);
-    return launch_cfg<T, STRICT, false, false, C>(p, s);
+    if (moments && resid) return launch_cfg<T, STRICT, true, true>(p, storage, s);
+    if (moments) return launch_cfg<T, STRICT, true, false>(p, storage, s);
+    if (resid) return launch_cfg<T, STRICT, false, true>(p, storage, s);
+    return launch_cfg<T, STRICT, false, false>(p, storage, s);
 }
 
 }  // namespace lbm
