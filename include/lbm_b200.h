@@ -217,7 +217,8 @@ int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max,
 /* ---- z-slab halo exchange: the 5 populations crossing each face ----
  * side 0 = low-z face (sends q with c_z=-1, receives c_z=+1), side 1 = high-z.
  * lbm_halo_buffers returns DEVICE pointers to the contiguous send / receive
- * staging buffers of that side (5 * nx_pitch * ny reals) for the caller's
+ * staging buffers of that side (dense storage: 5 * nx_pitch * ny reals each; sparse storage: 5 reals per
+ * stored node of the outermost owned plane / of the halo plane, so the two sizes differ) for the caller's
  * transport (NCCL send/recv, or a peer GPU's kernel storing straight into it).
  * lbm_step_begin .. lbm_step_end bracket one step:
  *   begin:    face planes computed first, send buffers packed (async on the handle's stream)
@@ -225,7 +226,8 @@ int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max,
  *   interior: the remaining planes, overlapping the transfer (implied by end if omitted)
  *   <caller makes the handle's stream wait for the transfers>
  *   end:      received populations unpacked into the halo planes, buffers swap. */
-int lbm_halo_buffers(lbm_handle h, int32_t side, void **send_dev, void **recv_dev, size_t *bytes);
+int lbm_halo_buffers(lbm_handle h, int32_t side, void **send_dev, void **recv_dev, size_t *send_bytes,
+                     size_t *recv_bytes);
 #define LBM_STEP_MOMENTS 1 /* materialise rho,u on this step (bif:592-595) */
 #define LBM_STEP_VELSUM 2  /* also accumulate S = sum|u| for lbm_last_velsum (ldc:660-662) */
 int lbm_step_begin(lbm_handle h, int32_t flags);

@@ -121,7 +121,7 @@ def load_library() -> C.CDLL:
         "lbm_output_save": ([vp, i32], C.c_int),
         "lbm_run_fixed": ([vp, i32, i32, i32], C.c_int),
         "lbm_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
-        "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t)], C.c_int),
+        "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t), P(C.c_size_t)], C.c_int),
         "lbm_step_begin": ([vp, i32], C.c_int),
         "lbm_step_interior": ([vp], C.c_int),
         "lbm_step_end": ([vp], C.c_int),
@@ -249,9 +249,9 @@ class Case:
         return v.value
 
     def halo_buffers(self, side: int):
-        s, r, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
-        self._ck(self._L.lbm_halo_buffers(self._h, side, C.byref(s), C.byref(r), C.byref(n)))
-        return s.value, r.value, n.value
+        s, r, ns, nr = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+        self._ck(self._L.lbm_halo_buffers(self._h, side, C.byref(s), C.byref(r), C.byref(ns), C.byref(nr)))
+        return s.value, r.value, ns.value, nr.value
 
     def residual(self, kind: int = RES_VELSUM) -> float:
         v = C.c_double()

@@ -59,7 +59,7 @@ struct SolverBase {
     virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
-    virtual int halo_buffers(int side, void **send, void **recv, size_t *bytes) = 0;
+    virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
     virtual int sync() = 0;
     virtual void *stream_ptr() = 0;
     int64_t steps = 0, launches = 0, nfluid = 0, dev_bytes = 0;
@@ -116,6 +116,18 @@ struct Solver final : SolverBase {
     double last_S = 0.0;
     long long pend_i0 = 0, pend_i1 = 0;
     bool interior_pending = false;
+    // sparse storage (reference compact order + run segments)
+    bool sparse = false;
+    long long n_lo_stored = 0, stored_box = 0;   // stored nodes of the low halo plane / of the whole state box
+    long long sp_first = 0;                      // global compact id of the first stored node of the state box
+    long long nseg = 0;
+    long long *d_cart = nullptr, *d_chunk_off = nullptr;
+    uint32_t *d_nodec = nullptr;
+    int8_t *d_labelc = nullptr;
+    int32_t *d_rec = nullptr, *d_chunk_cnt = nullptr;
+    std::vector<long long> seg_plane_start;      // [owned planes + 1]
+    long long halo_id0[2] = {0, 0}, halo_n[2] = {0, 0};   // compact range of the halo plane per side
+    long long face_id0[2] = {0, 0}, face_n[2] = {0, 0};   // compact range of the outermost owned plane per side
 
     ~Solver() override {
         cudaSetDevice(d.device);
@@ -125,6 +137,7 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
+        fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -289,10 +302,12 @@ struct Solver final : SolverBase {
         }
         CK(launch_node_words(d_label, d_node, d_seg, d_label8, box, own_z0, own_z1, fluid_label, d_cnt + 3, st));
         launches++;
-        long long nf = 0;
+        long long nf = 0, nbox = 0;
         CK(cudaMemcpyAsync(&nf, d_cnt + 3, sizeof nf, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&nbox, d_cnt + 2, sizeof nbox, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         nfluid = nf;
+        n_lo_stored = n_lo, stored_box = nbox, sp_first = (long long)compact_first - n_lo;
         have_index = true;
         if (nlat) *nlat = compact_total;
         return 0;
@@ -360,8 +375,9 @@ struct Solver final : SolverBase {
     int initialize() override {
         if (!have_index) FAIL(LBM_ERR_STATE, "initialize before index_transform");
         CK(cudaSetDevice(d.device));
+        if (d.storage == LBM_STORE_SPARSE_AB) return initialize_sparse();
         if (d.storage != LBM_STORE_DENSE_AB && d.storage != LBM_STORE_DENSE_AA)
-            FAIL(LBM_ERR_ARG, "storage %d not available in this build", d.storage);
+            FAIL(LBM_ERR_ARG, "unknown storage %d", d.storage);
         const bool aa = d.storage == LBM_STORE_DENSE_AA;
         if (aa && (lo_halo || hi_halo)) FAIL(LBM_ERR_ARG, "in-place (AA) storage is single-domain only in this build");
         if (d.case_rule == LBM_CASE_GEO_Y_INOUT && !have_planes) {
@@ -409,6 +425,84 @@ struct Solver final : SolverBase {
         return 0;
     }
 
+    long long count_plane(int zl) {
+        long long c = 0;
+        if (launch_count_stored(d_label + (long long)zl * box.plane, box.plane, box.px, box.nx, store_all(), d_cnt + 4, st) !=
+            cudaSuccess)
+            return -1;
+        launches++;
+        cudaMemcpyAsync(&c, d_cnt + 4, sizeof c, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        return c;
+    }
+
+    // populations / moments / node words in the reference's compact order, run-segment records
+    int initialize_sparse() {
+        sparse = true;
+        if (!d_plane_in) {
+            if (!have_planes) h_in.assign((size_t)d.nx * d.nz, 0.f), h_out = h_in;
+            int r = upload_planes();
+            if (r) return r;
+        }
+        const long long ns = stored_box;
+        const int nzl = box.z1 - box.z0, nown = own_z1 - own_z0;
+        if (!d_cart) {
+            if (dalloc(&d_cart, (size_t)ns) || dalloc(&d_nodec, (size_t)ns) || dalloc(&d_labelc, (size_t)ns)) return LBM_ERR_NOMEM;
+        }
+        CK(launch_compact_maps(d_index, d_node, d_label, box.cells(), sp_first, d_cart, d_nodec, d_labelc, st));
+        launches++;
+        // segments of the owned planes
+        const long long nchunks = (long long)nown * box.plane / 32;
+        if (!d_chunk_cnt && (dalloc(&d_chunk_cnt, (size_t)nchunks) || dalloc(&d_chunk_off, (size_t)nchunks))) return LBM_ERR_NOMEM;
+        CK(launch_build_segments(d_node, d_index, box, own_z0, own_z1, sp_first, d_chunk_cnt, d_chunk_off, d_cnt + 5, nullptr, st));
+        launches += 2;
+        CK(cudaMemcpyAsync(&nseg, d_cnt + 5, sizeof nseg, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (d_rec) cudaFree(d_rec), d_rec = nullptr;
+        if (dalloc(&d_rec, (size_t)std::max<long long>(nseg, 1) * SEG_REC)) return LBM_ERR_NOMEM;
+        CK(launch_build_segments(d_node, d_index, box, own_z0, own_z1, sp_first, d_chunk_cnt, d_chunk_off, d_cnt + 5, d_rec, st));
+        launches++;
+        {
+            // first segment of every owned plane (chunks are in plane order)
+            std::vector<long long> off((size_t)nchunks);
+            CK(cudaMemcpyAsync(off.data(), d_chunk_off, (size_t)nchunks * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const long long cpp = box.plane / 32;
+            seg_plane_start.assign((size_t)nown + 1, nseg);
+            for (int z = 0; z < nown; z++) seg_plane_start[z] = off[(size_t)z * cpp];
+        }
+        // compact ranges of the halo planes and of the outermost owned planes
+        const int zl_first = own_z0 - box.z0, zl_last = own_z1 - 1 - box.z0;
+        halo_id0[0] = 0, halo_n[0] = lo_halo ? n_lo_stored : 0;
+        face_id0[0] = n_lo_stored, face_n[0] = lo_halo ? count_plane(zl_first) : 0;
+        halo_n[1] = hi_halo ? count_plane(nzl - 1) : 0, halo_id0[1] = ns - halo_n[1];
+        face_n[1] = hi_halo ? count_plane(zl_last) : 0, face_id0[1] = ns - halo_n[1] - face_n[1];
+        qstride = ns + 64;
+        if (!d_fa) {
+            const size_t fsize = (size_t)qstride * Q + 64;
+            if (dalloc(&d_fa, fsize) || dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
+            if (dalloc(&d_rho, (size_t)ns) || dalloc(&d_ux, (size_t)ns) || dalloc(&d_uy, (size_t)ns) || dalloc(&d_uz, (size_t)ns))
+                return LBM_ERR_NOMEM;
+            for (int sd = 0; sd < 2; sd++) {
+                const size_t nb = (size_t)std::max(face_n[sd], halo_n[sd]) * 5;
+                if (dalloc(&d_send[sd], nb) || dalloc(&d_recv[sd], nb)) return LBM_ERR_NOMEM;
+            }
+        }
+        InitParams<T> ip{};
+        ip.fa = d_fa, ip.fb = d_fb, ip.aa = 0, ip.qstride = qstride, ip.label = d_label;
+        ip.rho = d_rho, ip.ux = d_ux, ip.uy = d_uy, ip.uz = d_uz;
+        ip.box = box, ip.case_rule = d.case_rule, ip.u_max = (T)d.u_max;
+        for (int i = 0; i < LBM_MAX_BC; i++) ip.bc[i] = bc[i];
+        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out;
+        CK(launch_init_sparse<T>(ip, d_cart, ns, st));
+        launches++;
+        CK(cudaStreamSynchronize(st));
+        d_cur = d_fa, d_nxt = d_fb;
+        steps = 0;
+        have_init = true, have_moments = false, in_step = false;
+        return 0;
+    }
+
     StepParams<T> make_params(long long c0, long long c1, double *acc) {
         StepParams<T> p{};
         p.src = d_cur, p.dst = d_nxt, p.qstride = qstride;
@@ -436,6 +530,17 @@ struct Solver final : SolverBase {
     int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc) {
         if (c1 <= c0) return 0;
         StepParams<T> p = make_params(c0, c1, acc);
+        if (sparse) {
+            SparseParams<T> sp{};
+            sp.base = p, sp.rec = d_rec, sp.nodec = d_nodec;
+            const long long zA = c0 / box.plane - (own_z0 - box.z0), zB = c1 / box.plane - (own_z0 - box.z0);
+            sp.seg_begin = seg_plane_start[(size_t)zA], sp.seg_end = seg_plane_start[(size_t)zB];
+            if (sp.seg_end <= sp.seg_begin) return 0;
+            if (d.math == LBM_MATH_STRICT) CK(launch_step_sparse_strict<T>(sp, moments, resid, st));
+            else CK(launch_step_sparse_fast<T>(sp, moments, resid, st));
+            launches++;
+            return 0;
+        }
         if (d.math == LBM_MATH_STRICT) CK(launch_step_dense_strict<T>(p, moments, resid, d.storage, st));
         else CK(launch_step_dense_fast<T>(p, moments, resid, d.storage, st));
         launches++;
@@ -480,7 +585,8 @@ struct Solver final : SolverBase {
         long long i0 = plane_c(own_z0), i1 = plane_c(own_z1);
         if (hi_halo) {
             if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, d_acc))) return r;
-            CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
+            if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[1], face_n[1], 1, d_send[1], face_n[1], st));
+            else CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
             launches++;
             i1 = plane_c(zt);
         }
@@ -489,7 +595,8 @@ struct Solver final : SolverBase {
             i0 = plane_c(zb + 1);
         }
         if (lo_halo) {
-            CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
+            if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[0], face_n[0], 0, d_send[0], face_n[0], st));
+            else CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
             launches++;
         }
         pend_i0 = i0, pend_i1 = i1, interior_pending = true;
@@ -513,11 +620,13 @@ struct Solver final : SolverBase {
             if (r) return r;
         }
         if (lo_halo) {
-            CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
+            if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[0], halo_n[0], 0, d_recv[0], halo_n[0], st));
+            else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
             launches++;
         }
         if (hi_halo) {
-            CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
+            if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[1], halo_n[1], 1, d_recv[1], halo_n[1], st));
+            else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
             launches++;
         }
         if (step_flags & LBM_STEP_VELSUM) {
@@ -534,21 +643,27 @@ struct Solver final : SolverBase {
         *v = last_S;
         return 0;
     }
-    int halo_buffers(int side, void **send, void **recv, size_t *bytes) override {
+    int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) override {
         if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
         if (!have_init) FAIL(LBM_ERR_STATE, "halo_buffers before initialize");
         const bool present = side == 0 ? lo_halo : hi_halo;
         if (send) *send = present ? d_send[side] : nullptr;
         if (recv) *recv = present ? d_recv[side] : nullptr;
-        if (bytes) *bytes = present ? (size_t)box.plane * 5 * sizeof(T) : 0;
+        const size_t dense_b = (size_t)box.plane * 5 * sizeof(T);
+        if (send_bytes) *send_bytes = !present ? 0 : (sparse ? (size_t)face_n[side] * 5 * sizeof(T) : dense_b);
+        if (recv_bytes) *recv_bytes = !present ? 0 : (sparse ? (size_t)halo_n[side] * 5 * sizeof(T) : dense_b);
         return 0;
     }
 
     int residual(int kind, double *v) override {
         if (!have_moments) FAIL(LBM_ERR_STATE, "no moments yet: run lbm_step first");
         CK(cudaSetDevice(d.device));
-        CK(launch_reduce_fields<T>(d_ux, d_uy, d_uz, d_label, box, own_z0, own_z1, kind, fluid_label, d.case_rule,
-                                   d_acc + 1, st));
+        if (sparse)
+            CK(launch_reduce_fields_sparse<T>(d_ux, d_uy, d_uz, d_labelc, d_cart, box, n_lo_stored, n_lo_stored + stored_own,
+                                              kind, fluid_label, d.case_rule, d_acc + 1, st));
+        else
+            CK(launch_reduce_fields<T>(d_ux, d_uy, d_uz, d_label, box, own_z0, own_z1, kind, fluid_label, d.case_rule,
+                                       d_acc + 1, st));
         launches++;
         CK(cudaMemcpyAsync(v, d_acc + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -576,6 +691,16 @@ struct Solver final : SolverBase {
         if (!have_init) FAIL(LBM_ERR_STATE, "get_fields before initialize");
         CK(cudaSetDevice(d.device));
         const size_t n = (size_t)stored_own;
+        if (sparse) {  // the device arrays already are in compact order
+            const T *srcs[4] = {d_rho, d_ux, d_uy, d_uz};
+            void *dsts[4] = {rho, ux, uy, uz};
+            for (int k = 0; k < 4; k++)
+                if (dsts[k]) CK(cudaMemcpyAsync(dsts[k], srcs[k] + n_lo_stored, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (first) *first = compact_first;
+            if (count) *count = stored_own;
+            return 0;
+        }
         T *tmp = nullptr;
         CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * 4 * sizeof(T)));
         cudaError_t e = cudaMemsetAsync(tmp, 0, n * 4 * sizeof(T), st);
@@ -597,6 +722,13 @@ struct Solver final : SolverBase {
         if (!have_init) FAIL(LBM_ERR_STATE, "get_populations before initialize");
         CK(cudaSetDevice(d.device));
         const size_t n = (size_t)stored_own;
+        if (sparse) {  // d_scr itself, q-major
+            for (int q = 0; q < Q; q++)
+                CK(cudaMemcpyAsync((T *)f + (size_t)q * n, d_cur + (size_t)q * qstride + n_lo_stored, n * sizeof(T),
+                                   cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            return 0;
+        }
         T *tmp = nullptr;
         CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * Q * sizeof(T)));
         const int layout = d.storage == LBM_STORE_DENSE_AA ? ((steps & 1) ? 2 : 1) : 0;
@@ -1003,9 +1135,9 @@ int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max,
     H_OR_FAIL;
     return h->s->run_converge(max_it, tol, stag_max, time_save, wf, its, res);
 }
-int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_t *bytes) {
+int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) {
     H_OR_FAIL;
-    return h->s->halo_buffers(side, send, recv, bytes);
+    return h->s->halo_buffers(side, send, recv, send_bytes, recv_bytes);
 }
 int lbm_step_begin(lbm_handle h, int32_t flags) { H_OR_FAIL; return h->s->step_begin(flags); }
 int lbm_step_interior(lbm_handle h) { H_OR_FAIL; return h->s->step_interior(); }

@@ -445,6 +445,155 @@ __global__ void k_halo_unpack(T *f, long long qstride, const int8_t *label8, int
     for (int k = 0; k < 5; k++) f[(long long)halo_q(1 - side, k) * qstride + c] = buf[(long long)k * b.plane + i];
 }
 
+// ---------------------------------------------------------------- sparse storage
+// LBM_STORE_SPARSE_AB keeps the populations in the reference's own compact order
+// (one entry per stored node, geo != 0).  A "segment" is a run of <= 32 consecutive
+// FLUID cells of one row inside one aligned 32-cell chunk.  Every source of a fluid
+// node is a stored node (the -1 marking guarantees it) and consecutive stored x
+// positions have consecutive compact ids, so for each direction the sources of a
+// segment are one contiguous run of compact ids: a segment needs 19 base ids, not
+// 19 ids per node.  Record layout (24 x int32):
+//   [0..18] local compact id of the source of the segment's FIRST node per direction
+//           ([0] = the node itself), [19] length, [20],[21] Cartesian cell id of the
+//           first node (lo, hi), [22] 1 if any node of the run has a boundary link.
+__global__ void k_seg_count(const uint32_t *node, long long c0, long long c1, int32_t *counts) {
+    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // c0,c1 multiples of 32
+    bool fluid = c < c1 && !(node[c] & NODE_SKIP);
+    unsigned m = __ballot_sync(0xffffffffu, fluid);
+    if ((threadIdx.x & 31) == 0 && c < c1) counts[(c - c0) >> 5] = __popc(m & ~(m << 1));  // run starts
+}
+__global__ void k_seg_fill(const uint32_t *node, const int32_t *index, Box b, long long c0, long long c1,
+                           long long id_first, const long long *chunk_offset, int32_t *rec) {
+    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t w = c < c1 ? node[c] : NODE_SKIP;
+    bool fluid = !(w & NODE_SKIP);
+    unsigned m = __ballot_sync(0xffffffffu, fluid);
+    unsigned links = __ballot_sync(0xffffffffu, fluid && (w & NODE_LINKS));
+    if (c >= c1) return;
+    unsigned starts = m & ~(m << 1);
+    if (!((starts >> lane) & 1u)) return;                 // one thread per run: its first lane
+    unsigned after = (~m) >> lane;                         // first non-fluid lane at or after me
+    int len = after ? __ffs(after) - 1 : 32 - lane;
+    unsigned runmask = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << lane;
+    long long seg = chunk_offset[(c - c0) >> 5] + __popc(starts & ((1u << lane) - 1u));
+    int32_t *r = rec + seg * 24;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const long long s = c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
+        // every source of a fluid node is stored when the mask came from geo_pre; an
+        // unstored one (the reference would read d_scr[q*NLATTICE-1]) is clamped for memory safety
+        const long long id = (long long)index[s] - id_first;
+        r[q] = (int32_t)(id < 0 ? 0 : id);
+    }
+    r[19] = len;
+    r[20] = (int32_t)(c & 0xffffffffLL);
+    r[21] = (int32_t)(c >> 32);
+    r[22] = (links & runmask) ? 1 : 0;
+    r[23] = 0;
+}
+// exclusive scan of int32 counts into int64 offsets (single block, carry across chunks)
+__global__ void k_scan_i32(const int32_t *counts, long long *offsets, long long n, long long *total_out) {
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (long long start = 0; start < n; start += SCAN_BLOCK) {
+        long long i = start + threadIdx.x;
+        int v = i < n ? counts[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        if (i < n) offsets[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+// compact id -> Cartesian cell, node word and int8 label per stored node of the state box
+__global__ void k_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
+                               long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    int i = index[c];
+    if (i < 0) return;
+    long long o = (long long)i - id_first;
+    cart[o] = c;
+    nodec[o] = node[c];
+    labelc[o] = (int8_t)label[c];
+}
+template <typename T>
+__global__ void k_init_sparse(const __grid_constant__ InitParams<T> p, const long long *cart, long long nstored) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nstored) return;
+    const Box &b = p.box;
+    const long long c = cart[i];
+    Coord co = coord_of(b, c);
+    T ux, uy, uz, feq[Q];
+    init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, p.label[c], co.x, co.y, co.z, ux, uy, uz);
+    if (p.case_rule == LBM_CASE_LDC) {
+        feq_all_ldc_init<T>(T(1.0), ux, uy, uz, feq);
+    } else {
+        const T r3 = T(1.0) / T(3.0), r18 = T(1.0) / T(18.0), r36 = T(1.0) / T(36.0);
+#pragma unroll
+        for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        p.fa[(long long)q * p.qstride + i] = feq[q];
+        p.fb[(long long)q * p.qstride + i] = feq[q];
+    }
+    p.rho[i] = T(0), p.ux[i] = T(0), p.uy[i] = T(0), p.uz[i] = T(0);
+}
+// reductions over compact arrays (see k_reduce_fields)
+template <typename T>
+__global__ void k_reduce_fields_sparse(const T *ux, const T *uy, const T *uz, const int8_t *labelc, const long long *cart,
+                                       Box b, long long i0, long long i1, int kind, int fluid_label, int case_rule,
+                                       double *out) {
+    long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (i < i1) {
+        int g = labelc[i];
+        T s = ux[i] * ux[i] + uy[i] * uy[i] + uz[i] * uz[i];
+        if (kind == 0) {
+            if (g == fluid_label) v = (double)(T)sqrt((double)s);
+        } else {
+            Coord p = coord_of(b, cart[i]);
+            bool ok = case_rule == LBM_CASE_GEO_OPENINGS ? (g == 4) : (g >= 4);
+            if (case_rule == LBM_CASE_LDC) ok = g == fluid_label;
+            bool trimmed = p.x >= 1 && p.x <= b.nx - 2 && p.y >= 2 && p.y <= b.ny - 3 && p.z >= 1 && p.z <= b.nz - 2;
+            if (ok && trimmed) v = (double)s;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += ws[k];
+        if (t != 0.0) atomicAdd(out, t);
+    }
+}
+// halo planes in compact storage: a plane's stored nodes are one contiguous id range
+template <typename T>
+__global__ void k_halo_pack_sparse(const T *f, long long qstride, long long i0, long long n, int side, T *buf,
+                                   long long bufstride) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 5; k++) buf[(long long)k * bufstride + i] = f[(long long)halo_q(side, k) * qstride + i0 + i];
+}
+template <typename T>
+__global__ void k_halo_unpack_sparse(T *f, long long qstride, const int8_t *labelc, int fluid_label, long long i0,
+                                     long long n, int side, const T *buf, long long bufstride) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (labelc[i0 + i] != fluid_label) return;
+#pragma unroll
+    for (int k = 0; k < 5; k++) f[(long long)halo_q(1 - side, k) * qstride + i0 + i] = buf[(long long)k * bufstride + i];
+}
+
 inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -543,6 +692,57 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
     return cudaGetLastError();
 }
 
+// ---- sparse storage
+cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Box box, int own_z0, int own_z1,
+                                  long long id_first, int32_t *counts, long long *offsets, long long *nseg_dev,
+                                  int32_t *rec, cudaStream_t s) {
+    const long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
+    const long long nchunks = (c1 - c0) >> 5;
+    if (nchunks <= 0) return cudaSuccess;
+    if (!rec) {  // pass 1: count runs per chunk and scan
+        k_seg_count<<<nblocks(c1 - c0, 256), 256, 0, s>>>(node, c0, c1, counts);
+        k_scan_i32<<<1, SCAN_BLOCK, 0, s>>>(counts, offsets, nchunks, nseg_dev);
+    } else {     // pass 2: fill the records
+        k_seg_fill<<<nblocks(c1 - c0, 256), 256, 0, s>>>(node, index, box, c0, c1, id_first, offsets, rec);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
+                                long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc, cudaStream_t s) {
+    k_compact_maps<<<nblocks(cells, 256), 256, 0, s>>>(index, node, label, cells, id_first, cart, nodec, labelc);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_init_sparse(const InitParams<T> &p, const long long *cart, long long nstored, cudaStream_t s) {
+    if (nstored <= 0) return cudaSuccess;
+    k_init_sparse<T><<<nblocks(nstored, 128), 128, 0, s>>>(p, cart, nstored);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_reduce_fields_sparse(const T *ux, const T *uy, const T *uz, const int8_t *labelc, const long long *cart,
+                                        Box box, long long i0, long long i1, int kind, int fluid_label, int case_rule,
+                                        double *out_dev, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out_dev, 0, sizeof(double), s);
+    if (e != cudaSuccess || i1 <= i0) return e;
+    k_reduce_fields_sparse<T><<<nblocks(i1 - i0, 256), 256, 0, s>>>(ux, uy, uz, labelc, cart, box, i0, i1, kind,
+                                                                   fluid_label, case_rule, out_dev);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_halo_pack_sparse(const T *f, long long qstride, long long i0, long long n, int side, T *buf,
+                                    long long bufstride, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_halo_pack_sparse<T><<<nblocks(n, 256), 256, 0, s>>>(f, qstride, i0, n, side, buf, bufstride);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_halo_unpack_sparse(T *f, long long qstride, const int8_t *labelc, int fluid_label, long long i0,
+                                      long long n, int side, const T *buf, long long bufstride, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_halo_unpack_sparse<T><<<nblocks(n, 256), 256, 0, s>>>(f, qstride, labelc, fluid_label, i0, n, side, buf, bufstride);
+    return cudaGetLastError();
+}
+
 #define LBM_INST(T)                                                                                                     \
     template cudaError_t launch_init<T>(const InitParams<T> &, cudaStream_t);                                           \
     template cudaError_t launch_gather_fields<T>(const T *, const T *, const T *, const T *, const int32_t *,           \
@@ -553,6 +753,14 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
     template cudaError_t launch_reduce_fields<T>(const T *, const T *, const T *, const int32_t *, Box, int, int, int,  \
                                                  int, int, double *, cudaStream_t);                                     \
     template cudaError_t launch_halo_pack<T>(const T *, long long, Box, int, int, T *, cudaStream_t);                   \
+    template cudaError_t launch_init_sparse<T>(const InitParams<T> &, const long long *, long long, cudaStream_t);      \
+    template cudaError_t launch_reduce_fields_sparse<T>(const T *, const T *, const T *, const int8_t *,                \
+                                                        const long long *, Box, long long, long long, int, int, int,   \
+                                                        double *, cudaStream_t);                                        \
+    template cudaError_t launch_halo_pack_sparse<T>(const T *, long long, long long, long long, int, T *, long long,   \
+                                                    cudaStream_t);                                                      \
+    template cudaError_t launch_halo_unpack_sparse<T>(T *, long long, const int8_t *, int, long long, long long, int,   \
+                                                      const T *, long long, cudaStream_t);                              \
     template cudaError_t launch_halo_unpack<T>(T *, long long, const int8_t *, int, Box, int, int, const T *,           \
                                                cudaStream_t);
 LBM_INST(float)

@@ -114,7 +114,41 @@ template <typename T>
 cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box box, int zl, int side,
                                const T *buf, cudaStream_t s);
 
+// ---- sparse storage (reference compact order + run segments), lbm_geo.cu
+constexpr int SEG_REC = 24;  // int32 per segment record, see k_seg_fill
+// pass 1 (rec == nullptr): per-chunk run counts + scan (nseg to *nseg_dev); pass 2: fill the records
+cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Box box, int own_z0, int own_z1,
+                                  long long id_first, int32_t *counts, long long *offsets, long long *nseg_dev,
+                                  int32_t *rec, cudaStream_t s);
+cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
+                                long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc, cudaStream_t s);
+template <typename T>
+cudaError_t launch_init_sparse(const InitParams<T> &p, const long long *cart, long long nstored, cudaStream_t s);
+template <typename T>
+cudaError_t launch_reduce_fields_sparse(const T *ux, const T *uy, const T *uz, const int8_t *labelc, const long long *cart,
+                                        Box box, long long i0, long long i1, int kind, int fluid_label, int case_rule,
+                                        double *out_dev, cudaStream_t s);
+template <typename T>
+cudaError_t launch_halo_pack_sparse(const T *f, long long qstride, long long i0, long long n, int side, T *buf,
+                                    long long bufstride, cudaStream_t s);
+template <typename T>
+cudaError_t launch_halo_unpack_sparse(T *f, long long qstride, const int8_t *labelc, int fluid_label, long long i0,
+                                      long long n, int side, const T *buf, long long bufstride, cudaStream_t s);
+
+// everything the sparse step needs
+template <typename T>
+struct SparseParams {
+    StepParams<T> base;      // src/dst (compact), qstride = stored nodes of the state box, box, bc, ...
+    const int32_t *rec;      // [nseg][SEG_REC]
+    const uint32_t *nodec;   // node words by compact id
+    long long seg_begin, seg_end;
+};
+
 // fused step (lbm_step_fast.cu / lbm_step_strict.cu)
+template <typename T>
+cudaError_t launch_step_sparse_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
+template <typename T>
+cudaError_t launch_step_sparse_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s);
 template <typename T>

@@ -10,3 +10,13 @@ cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool re
 template cudaError_t launch_step_dense_fast<float>(const StepParams<float> &, bool, bool, int, cudaStream_t);
 template cudaError_t launch_step_dense_fast<double>(const StepParams<double> &, bool, bool, int, cudaStream_t);
 }  // namespace lbm
+
+#include "step_sparse.cuh"
+namespace lbm {
+template <typename T>
+cudaError_t launch_step_sparse_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
+    return launch_step_sparse_impl<T, false>(p, moments, resid, s);
+}
+template cudaError_t launch_step_sparse_fast<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
+template cudaError_t launch_step_sparse_fast<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+}  // namespace lbm

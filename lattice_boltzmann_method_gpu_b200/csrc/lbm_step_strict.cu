@@ -14,3 +14,13 @@ cudaError_t launch_step_dense_strict(const StepParams<T> &p, bool moments, bool 
 template cudaError_t launch_step_dense_strict<float>(const StepParams<float> &, bool, bool, int, cudaStream_t);
 template cudaError_t launch_step_dense_strict<double>(const StepParams<double> &, bool, bool, int, cudaStream_t);
 }  // namespace lbm
+
+#include "step_sparse.cuh"
+namespace lbm {
+template <typename T>
+cudaError_t launch_step_sparse_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
+    return launch_step_sparse_impl<T, true>(p, moments, resid, s);
+}
+template cudaError_t launch_step_sparse_strict<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
+template cudaError_t launch_step_sparse_strict<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+}  // namespace lbm

@@ -1,0 +1,90 @@
+// Fused step on the SPARSE storage: populations, moments and node words live in the reference's own
+// compact order (one entry per stored node, index_transform numbering, bifurcation.cu:241-252), two
+// buffers, addressed through run-segment records instead of a per-node neighbour list.
+//
+// One warp = one segment = a run of <= 32 consecutive fluid nodes of one row.  For each direction the
+// sources of the run are one contiguous range of compact ids (every source of a fluid node is a stored
+// node, and consecutive stored x positions have consecutive ids), so the warp needs the record's 19
+// base ids (one 96-byte load, broadcast by shuffles) and then issues 19 coalesced loads -- 2.5 B of
+// index traffic per node instead of the 72 B of an 18-entry neighbour list.
+//
+// Boundary links work exactly as in step_dense.cuh: the slot of link q is the pull source itself,
+// dst[q][base_q + lane] -- wall, inlet/outlet and -1 nodes ARE stored nodes in this layout, as in the
+// reference.  The slow path (inlet/outlet/lid/static) is the same out-of-line function, fed with the
+// node's Cartesian cell id from the record.
+#pragma once
+#include "step_dense.cuh"
+
+namespace lbm {
+
+constexpr int SPARSE_BLOCK = 128;
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID>
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
+    k_step_sparse(const __grid_constant__ SparseParams<T> sp) {
+    const StepParams<T> &p = sp.base;
+    const int lane = threadIdx.x & 31;
+    const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
+    if (seg >= sp.seg_end) return;
+    const int32_t r = lane < SEG_REC ? sp.rec[seg * SEG_REC + lane] : 0;
+    const int len = __shfl_sync(0xffffffffu, r, 19);
+    const bool active = lane < len;
+    int base[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) base[q] = __shfl_sync(0xffffffffu, r, q);
+    const unsigned clo = (unsigned)__shfl_sync(0xffffffffu, r, 20), chi = (unsigned)__shfl_sync(0xffffffffu, r, 21);
+    const int has_links = __shfl_sync(0xffffffffu, r, 22);
+    double velsum = 0.0;
+    if (active) {
+        const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
+        const long long i = (long long)base[0] + lane;                                   // compact id
+        const uint32_t node = has_links ? sp.nodec[i] : 0u;
+        T f[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) f[q] = ld_stream(p.src + (long long)q * p.qstride + base[q] + lane);
+        T rho, ux, uy, uz;
+        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+        T *dst = p.dst;
+#pragma unroll
+        for (int q = 0; q < Q; q++) dst[(long long)q * p.qstride + i] = f[q];
+        if (MOMENTS) {
+            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+        }
+        if (RESID) velsum = (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+        if (node & NODE_LINKS) {
+            if (node & NODE_WALLS_ONLY) {
+#pragma unroll
+                for (int q = 1; q < Q; q++)
+                    if (node & (1u << q)) dst[(long long)q * p.qstride + base[q] + lane] = f[oppq(q)];
+            } else {
+#pragma unroll
+                for (int q = 1; q < Q; q++) {
+                    if (node & (1u << q)) {
+                        T h;
+                        if (boundary_link<T>(p, c, q, MODE_AB, rho, ux, uy, uz, f[q], f[oppq(q)], &h))
+                            dst[(long long)q * p.qstride + base[q] + lane] = h;
+                    }
+                }
+            }
+        }
+    }
+    if (RESID) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
+        if (lane == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    }
+}
+
+template <typename T, bool STRICT>
+cudaError_t launch_step_sparse_impl(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
+    const long long n = p.seg_end - p.seg_begin;
+    if (n <= 0) return cudaSuccess;
+    const unsigned nb = (unsigned)((n + SPARSE_BLOCK / 32 - 1) / (SPARSE_BLOCK / 32));
+    if (moments && resid) k_step_sparse<T, STRICT, true, true><<<nb, SPARSE_BLOCK, 0, s>>>(p);
+    else if (moments) k_step_sparse<T, STRICT, true, false><<<nb, SPARSE_BLOCK, 0, s>>>(p);
+    else if (resid) k_step_sparse<T, STRICT, false, true><<<nb, SPARSE_BLOCK, 0, s>>>(p);
+    else k_step_sparse<T, STRICT, false, false><<<nb, SPARSE_BLOCK, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace lbm

@@ -109,12 +109,12 @@ class SlabCase(api.Case):
         self._ext = torch.cuda.ExternalStream(self.stream)
         bufs = []
         for side in (0, 1):
-            s, r, n = self.halo_buffers(side)
-            if n == 0:
+            s, r, ns, nr = self.halo_buffers(side)
+            if not s:
                 bufs.append((None, None))
-            else:
-                bufs.append((torch.as_tensor(_DevBuf(s, n, self.dtype), device="cuda"),
-                             torch.as_tensor(_DevBuf(r, n, self.dtype), device="cuda")))
+            else:  # an empty plane (sparse storage) still takes part in the exchange with 0-size-safe tensors
+                bufs.append((torch.as_tensor(_DevBuf(s, max(ns, self.dtype.itemsize), self.dtype), device="cuda")[: ns // self.dtype.itemsize],
+                             torch.as_tensor(_DevBuf(r, max(nr, self.dtype.itemsize), self.dtype), device="cuda")[: nr // self.dtype.itemsize]))
         self._bufs = bufs
 
     def _one_step(self, flags=0):

@@ -10,7 +10,7 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def run_slabs(name, n, P, steps, precision, math_mode, pulse=None):
+def run_slabs(name, n, P, steps, precision, math_mode, pulse=None, storage=None):
     import torch
 
     import lattice_boltzmann_method_gpu_b200 as L
@@ -18,7 +18,7 @@ def run_slabs(name, n, P, steps, precision, math_mode, pulse=None):
 
     nz = {"ldc": n, "pos": n, "bif": 32, "cor": 44}[name]
     ranges = slab.slab_ranges(nz, P)
-    cs = [H.gpu_case(name, n, precision, math_mode, pulse=pulse, z_range=r) for r in ranges]
+    cs = [H.gpu_case(name, n, precision, math_mode, pulse=pulse, z_range=r, storage=storage) for r in ranges]
     for c in cs:
         c.geo_pre()
     offs, total = slab.compact_offsets([c.local_stored_count() for c in cs])
@@ -30,11 +30,12 @@ def run_slabs(name, n, P, steps, precision, math_mode, pulse=None):
         c.initialize()
 
     def view(c, side):
-        s, r, nbytes = c.halo_buffers(side)
-        if nbytes == 0:
+        s, r, ns, nr = c.halo_buffers(side)
+        if not s:
             return None, None
-        mk = lambda p: torch.as_tensor(slab._DevBuf(p, nbytes, c.dtype), device="cuda")
-        return mk(s), mk(r)
+        it = c.dtype.itemsize
+        mk = lambda p, nb: torch.as_tensor(slab._DevBuf(p, max(nb, it), c.dtype), device="cuda")[: nb // it]
+        return mk(s, ns), mk(r, nr)
 
     bufs = [(view(c, 0), view(c, 1)) for c in cs]
     for it in range(steps):
