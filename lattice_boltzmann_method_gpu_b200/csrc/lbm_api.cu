@@ -99,7 +99,7 @@ struct Solver final : SolverBase {
     // device
     uint8_t *d_flag = nullptr;
     int32_t *d_label_ext = nullptr, *d_label = nullptr, *d_index = nullptr, *d_scratch = nullptr;
-    uint32_t *d_node = nullptr;
+    uint32_t *d_node = nullptr, *d_wall = nullptr, *d_wallc = nullptr;
     uint8_t *d_seg = nullptr;
     int8_t *d_label8 = nullptr;
     T *d_fa = nullptr, *d_fb = nullptr, *d_cur = nullptr, *d_nxt = nullptr;
@@ -137,7 +137,7 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
-        fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
+        fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -296,11 +296,11 @@ struct Solver final : SolverBase {
         launches += 3;
         // node words, segment classes, int8 labels
         if (!d_node) {
-            if (dalloc(&d_node, (size_t)box.cells()) || dalloc(&d_seg, (size_t)(box.cells() / 32 + 1)) ||
+            if (dalloc(&d_node, (size_t)box.cells()) || dalloc(&d_wall, (size_t)box.cells()) || dalloc(&d_seg, (size_t)(box.cells() / 32 + 1)) ||
                 dalloc(&d_label8, (size_t)box.cells()))
                 return LBM_ERR_NOMEM;
         }
-        CK(launch_node_words(d_label, d_node, d_seg, d_label8, box, own_z0, own_z1, fluid_label, d_cnt + 3, st));
+        CK(launch_node_words(d_label, d_node, d_wall, d_seg, d_label8, box, own_z0, own_z1, fluid_label, bc, d_cnt + 3, st));
         launches++;
         long long nf = 0, nbox = 0;
         CK(cudaMemcpyAsync(&nf, d_cnt + 3, sizeof nf, cudaMemcpyDeviceToHost, st));
@@ -447,9 +447,11 @@ struct Solver final : SolverBase {
         const long long ns = stored_box;
         const int nzl = box.z1 - box.z0, nown = own_z1 - own_z0;
         if (!d_cart) {
-            if (dalloc(&d_cart, (size_t)ns) || dalloc(&d_nodec, (size_t)ns) || dalloc(&d_labelc, (size_t)ns)) return LBM_ERR_NOMEM;
+            if (dalloc(&d_cart, (size_t)ns) || dalloc(&d_nodec, (size_t)ns) || dalloc(&d_wallc, (size_t)ns) ||
+                dalloc(&d_labelc, (size_t)ns))
+                return LBM_ERR_NOMEM;
         }
-        CK(launch_compact_maps(d_index, d_node, d_label, box.cells(), sp_first, d_cart, d_nodec, d_labelc, st));
+        CK(launch_compact_maps(d_index, d_node, d_wall, d_label, box.cells(), sp_first, d_cart, d_nodec, d_wallc, d_labelc, st));
         launches++;
         // segments of the owned planes
         const long long nchunks = (long long)nown * box.plane / 32;
@@ -506,7 +508,7 @@ struct Solver final : SolverBase {
     StepParams<T> make_params(long long c0, long long c1, double *acc) {
         StepParams<T> p{};
         p.src = d_cur, p.dst = d_nxt, p.qstride = qstride;
-        p.node = d_node, p.seg = d_seg, p.label8 = d_label8;
+        p.node = d_node, p.wall = d_wall, p.seg = d_seg, p.label8 = d_label8;
         p.rho = d_rho, p.ux = d_ux, p.uy = d_uy, p.uz = d_uz;
         p.resid = acc;
         p.box = box, p.c_begin = c0, p.c_end = c1;
@@ -532,7 +534,7 @@ struct Solver final : SolverBase {
         StepParams<T> p = make_params(c0, c1, acc);
         if (sparse) {
             SparseParams<T> sp{};
-            sp.base = p, sp.rec = d_rec, sp.nodec = d_nodec;
+            sp.base = p, sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc;
             const long long zA = c0 / box.plane - (own_z0 - box.z0), zB = c1 / box.plane - (own_z0 - box.z0);
             sp.seg_begin = seg_plane_start[(size_t)zA], sp.seg_end = seg_plane_start[(size_t)zB];
             if (sp.seg_end <= sp.seg_begin) return 0;

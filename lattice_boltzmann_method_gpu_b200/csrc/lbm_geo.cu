@@ -268,11 +268,14 @@ __global__ void k_count_stored(const int32_t *label, long long cells, StoredRule
 // ---------------------------------------------------------------- node words
 // One thread per cell of the state box.  Fluid nodes of the OWNED planes get
 // the 18 "source is not fluid" bits; everything else is NODE_SKIP.
-__global__ void k_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box b, int own_z0,
-                             int own_z1, int fluid_label, long long *nfluid) {
+struct BcTable {
+    BcEntry e[LBM_MAX_BC];
+};
+__global__ void k_node_words(const int32_t *label, uint32_t *node, uint32_t *wall, uint8_t *seg, int8_t *label8, Box b,
+                             int own_z0, int own_z1, int fluid_label, BcTable bc, long long *nfluid) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = c < b.cells();
-    uint32_t w = NODE_SKIP;
+    uint32_t w = NODE_SKIP, wm = 0;
     if (valid) {
         Coord p = coord_of(b, c);
         int g = label[c];
@@ -287,12 +290,16 @@ __global__ void k_node_words(const int32_t *label, uint32_t *node, uint8_t *seg,
                 int gs = inb ? label[cell_of(b, x, y, z)] : 0;
                 if (gs != fluid_label) {
                     w |= (1u << q);
-                    if (gs != 1) walls_only = false;
+                    if (gs == 1) wm |= (1u << q);
+                    else walls_only = false;
+                    if (gs >= 2 && gs < LBM_MAX_BC && bc.e[gs].kind != LBM_BC_NONE && caxis(q, bc.e[gs].naxis) == bc.e[gs].nsign)
+                        w |= NODE_HAS_BC;
                 }
             }
             if (w && walls_only) w |= NODE_WALLS_ONLY;
         }
         node[c] = w;
+        wall[c] = wm;
     }
     unsigned fluid_m = __ballot_sync(0xffffffffu, valid && !(w & NODE_SKIP));
     unsigned link_m = __ballot_sync(0xffffffffu, valid && (w & NODE_LINKS));
@@ -510,8 +517,9 @@ __global__ void k_scan_i32(const int32_t *counts, long long *offsets, long long 
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 // compact id -> Cartesian cell, node word and int8 label per stored node of the state box
-__global__ void k_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
-                               long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc) {
+__global__ void k_compact_maps(const int32_t *index, const uint32_t *node, const uint32_t *wall, const int32_t *label,
+                               long long cells, long long id_first, long long *cart, uint32_t *nodec, uint32_t *wallc,
+                               int8_t *labelc) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cells) return;
     int i = index[c];
@@ -519,6 +527,7 @@ __global__ void k_compact_maps(const int32_t *index, const uint32_t *node, const
     long long o = (long long)i - id_first;
     cart[o] = c;
     nodec[o] = node[c];
+    wallc[o] = wall[c];
     labelc[o] = (int8_t)label[c];
 }
 template <typename T>
@@ -638,12 +647,15 @@ cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, i
     k_count_stored<<<nblocks(cells, 256), 256, 0, s>>>(label, cells, sr, out_dev);
     return cudaGetLastError();
 }
-cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box box, int own_z0,
-                              int own_z1, int fluid_label, long long *nfluid_dev, cudaStream_t s) {
+cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint32_t *wall, uint8_t *seg, int8_t *label8, Box box,
+                              int own_z0, int own_z1, int fluid_label, const BcEntry *bc, long long *nfluid_dev,
+                              cudaStream_t s) {
+    BcTable t;
+    for (int i = 0; i < LBM_MAX_BC; i++) t.e[i] = bc[i];
     cudaError_t e = cudaMemsetAsync(nfluid_dev, 0, sizeof(long long), s);
     if (e != cudaSuccess) return e;
-    k_node_words<<<nblocks(box.cells(), 256), 256, 0, s>>>(label, node, seg, label8, box, own_z0, own_z1, fluid_label,
-                                                          nfluid_dev);
+    k_node_words<<<nblocks(box.cells(), 256), 256, 0, s>>>(label, node, wall, seg, label8, box, own_z0, own_z1, fluid_label,
+                                                          t, nfluid_dev);
     return cudaGetLastError();
 }
 template <typename T>
@@ -707,9 +719,10 @@ cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Bo
     }
     return cudaGetLastError();
 }
-cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
-                                long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc, cudaStream_t s) {
-    k_compact_maps<<<nblocks(cells, 256), 256, 0, s>>>(index, node, label, cells, id_first, cart, nodec, labelc);
+cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const uint32_t *wall, const int32_t *label,
+                                long long cells, long long id_first, long long *cart, uint32_t *nodec, uint32_t *wallc,
+                                int8_t *labelc, cudaStream_t s) {
+    k_compact_maps<<<nblocks(cells, 256), 256, 0, s>>>(index, node, wall, label, cells, id_first, cart, nodec, wallc, labelc);
     return cudaGetLastError();
 }
 template <typename T>

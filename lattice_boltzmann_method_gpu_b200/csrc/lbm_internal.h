@@ -18,6 +18,12 @@ constexpr uint32_t NODE_LINKS = 0x7FFFEu;
 //   bit 31       : every non-fluid source of this node is a wall (label 1): all its
 //                  links are plain half-way bounce-back, handled inline
 constexpr uint32_t NODE_WALLS_ONLY = 0x80000000u;
+//   bit 30       : at least one link of this node comes from an inlet/outlet/lid node and lies in
+//                  that boundary's direction set, i.e. needs the non-equilibrium extrapolation.
+//                  Without it every non-wall link is "static" (its slot is never rewritten).
+constexpr uint32_t NODE_HAS_BC = 0x40000000u;
+// second word per node ("wall mask"): bit q set <=> the source of direction q is a wall.  Only
+// read for nodes that have links and are not walls-only (curved walls: -1 outer neighbours).
 
 // per 32-cell segment summary (one warp of the dense kernels)
 enum : uint8_t { SEG_BULK = 0, SEG_MIXED = 1, SEG_EMPTY = 2 };
@@ -50,6 +56,7 @@ struct StepParams {
     T *dst;
     long long qstride;  // elements between consecutive populations
     const uint32_t *node;
+    const uint32_t *wall;  // wall mask per cell (dense) / per compact id (sparse)
     const uint8_t *seg;
     const int8_t *label8;
     T *rho, *ux, *uy, *uz;  // dense moments (written when MOMENTS)
@@ -93,8 +100,9 @@ cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells
 size_t compact_scratch_ints(long long cells);
 cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
                                 cudaStream_t s);
-cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint8_t *seg, int8_t *label8, Box box, int own_z0,
-                              int own_z1, int fluid_label, long long *nfluid_dev, cudaStream_t s);
+cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint32_t *wall, uint8_t *seg, int8_t *label8, Box box,
+                              int own_z0, int own_z1, int fluid_label, const BcEntry *bc, long long *nfluid_dev,
+                              cudaStream_t s);
 template <typename T>
 cudaError_t launch_init(const InitParams<T> &p, cudaStream_t s);
 template <typename T>
@@ -120,8 +128,9 @@ constexpr int SEG_REC = 24;  // int32 per segment record, see k_seg_fill
 cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Box box, int own_z0, int own_z1,
                                   long long id_first, int32_t *counts, long long *offsets, long long *nseg_dev,
                                   int32_t *rec, cudaStream_t s);
-cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const int32_t *label, long long cells,
-                                long long id_first, long long *cart, uint32_t *nodec, int8_t *labelc, cudaStream_t s);
+cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const uint32_t *wall, const int32_t *label,
+                                long long cells, long long id_first, long long *cart, uint32_t *nodec, uint32_t *wallc,
+                                int8_t *labelc, cudaStream_t s);
 template <typename T>
 cudaError_t launch_init_sparse(const InitParams<T> &p, const long long *cart, long long nstored, cudaStream_t s);
 template <typename T>
@@ -141,6 +150,7 @@ struct SparseParams {
     StepParams<T> base;      // src/dst (compact), qstride = stored nodes of the state box, box, bc, ...
     const int32_t *rec;      // [nseg][SEG_REC]
     const uint32_t *nodec;   // node words by compact id
+    const uint32_t *wallc;   // wall masks by compact id
     long long seg_begin, seg_end;
 };
 

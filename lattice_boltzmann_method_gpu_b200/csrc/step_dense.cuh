@@ -201,8 +201,11 @@ __device__ __forceinline__ long long slot_index(int q, long long c, long long qs
 
 // collide, store, moments, boundary links of one fluid cell whose post-streaming
 // populations are already in f[]
-template <typename T, bool STRICT, bool MOMENTS, bool RESID, int MODE>
-__device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c, uint32_t node, T (&f)[Q], double &velsum) {
+// WALL_READY: the caller already holds the node's wall mask in `wallw`; otherwise it is fetched here,
+// lazily, by the few nodes that need it
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, int MODE, bool WALL_READY>
+__device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c, uint32_t node, uint32_t wallw, T (&f)[Q],
+                                            double &velsum) {
     const Box &b = p.box;
     T rho, ux, uy, uz;
     collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
@@ -222,19 +225,22 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
     }
     if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
     if (node & NODE_LINKS) {
-        if (node & NODE_WALLS_ONLY) {
-            // half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
+        // wall links: half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
+        const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (WALL_READY ? wallw : p.wall[c]);
 #pragma unroll
-            for (int q = 1; q < Q; q++) {
-                if (node & (1u << q)) {
-                    const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                    dst[slot_index<MODE>(q, c, p.qstride, off)] = f[oppq(q)];
-                }
+        for (int q = 1; q < Q; q++) {
+            if (wl & (1u << q)) {
+                const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+                dst[slot_index<MODE>(q, c, p.qstride, off)] = f[oppq(q)];
             }
-        } else {
+        }
+        // what is left is an inlet/outlet/lid link (slow path) or a static link, whose slot is never
+        // rewritten -- except by the odd in-place step, which has to restore it
+        const uint32_t rest = node & NODE_LINKS & ~wl;
+        if (rest && ((node & NODE_HAS_BC) || MODE == MODE_AA_ODD)) {
 #pragma unroll
             for (int q = 1; q < Q; q++) {
-                if (node & (1u << q)) {
+                if (rest & (1u << q)) {
                     T h;
                     if (boundary_link<T>(p, c, q, MODE, rho, ux, uy, uz, f[q], f[oppq(q)], &h)) {
                         const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
     const long long c = p.c_begin + (long long)blockIdx.x * cfg_block(CFG) + threadIdx.x;
     if (c >= p.c_end) return;  // ranges are whole planes (multiples of 32 cells): warp-uniform
     T f[Q];
-    uint32_t node;
+    uint32_t node, wallw = 0u;
     const uint32_t kind = p.seg[c >> 5];
     if (SPEC) {
         // every thread pulls; the buffers carry guards so all addresses are mapped
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
     } else {
         if (kind == SEG_EMPTY) return;
         node = kind == SEG_MIXED ? p.node[c] : 0u;
+        wallw = kind == SEG_MIXED ? p.wall[c] : 0u;
     }
     double velsum = 0.0;
     if (!(node & NODE_SKIP)) {
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
                 f[q] = MODE == MODE_AB ? ld_stream(a) : *a;
             }
         }
-        finish_cell<T, STRICT, MOMENTS, RESID, MODE>(p, c, node, f, velsum);
+        finish_cell<T, STRICT, MOMENTS, RESID, MODE, !SPEC>(p, c, node, wallw, f, velsum);
     }
     if (RESID) {
         // warp shuffle tree, then one atomic per warp

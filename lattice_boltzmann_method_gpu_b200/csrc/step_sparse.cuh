@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
         const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
         const long long i = (long long)base[0] + lane;                                   // compact id
         const uint32_t node = has_links ? sp.nodec[i] : 0u;
+        const uint32_t wallw = has_links ? sp.wallc[i] : 0u;
         T f[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) f[q] = ld_stream(p.src + (long long)q * p.qstride + base[q] + lane);
@@ -52,14 +53,15 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
         }
         if (RESID) velsum = (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
         if (node & NODE_LINKS) {
-            if (node & NODE_WALLS_ONLY) {
+            const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : wallw;
 #pragma unroll
-                for (int q = 1; q < Q; q++)
-                    if (node & (1u << q)) dst[(long long)q * p.qstride + base[q] + lane] = f[oppq(q)];
-            } else {
+            for (int q = 1; q < Q; q++)
+                if (wl & (1u << q)) dst[(long long)q * p.qstride + base[q] + lane] = f[oppq(q)];
+            const uint32_t rest = node & NODE_LINKS & ~wl;  // inlet/outlet links (slow path) or static (nothing)
+            if (rest && (node & NODE_HAS_BC)) {
 #pragma unroll
                 for (int q = 1; q < Q; q++) {
-                    if (node & (1u << q)) {
+                    if (rest & (1u << q)) {
                         T h;
                         if (boundary_link<T>(p, c, q, MODE_AB, rho, ux, uy, uz, f[q], f[oppq(q)], &h))
                             dst[(long long)q * p.qstride + base[q] + lane] = h;
