@@ -151,6 +151,10 @@ const char *lbm_last_error(lbm_handle h); /* h may be NULL: last create() error 
 /* Supply the binary voxel field from memory instead of geo_path (Cartesian,
  * GLOBAL box; host pointer).  Optional. */
 int lbm_set_flag(lbm_handle h, const int32_t *flag_cartesian);
+/* Same for one z-slab of a large box: `flag` holds planes [z_first, z_first+z_count) only, one byte
+ * per voxel, [z][y][x].  The planes must cover this handle's owned range extended by 3 planes on
+ * each interior side (labels look 1 plane, the -1 marking 1 more, the halo 1 more). */
+int lbm_set_flag_slab(lbm_handle h, const uint8_t *flag, int32_t z_first, int32_t z_count);
 
 /* geo_pre(): ldc:468-502, pos:52-254, bif:36-239, cor:31-260.  Reads geo_path
  * unless lbm_set_flag was called (LDC / POISEUILLE masks are analytic).  Label

@@ -71,7 +71,7 @@ class LbmError(RuntimeError):
 
 # every symbol include/lbm_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "lbm_case_defaults", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_set_flag", "lbm_geo_pre",
+    "lbm_case_defaults", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_set_flag", "lbm_set_flag_slab", "lbm_geo_pre",
     "lbm_index_transform", "lbm_local_stored_count", "lbm_set_compact_offset", "lbm_read_vel", "lbm_set_bc_planes",
     "lbm_initialize", "lbm_step", "lbm_step_timed", "lbm_step_count", "lbm_launch_count", "lbm_residual",
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
@@ -100,6 +100,7 @@ def load_library() -> C.CDLL:
         "lbm_destroy": ([vp], C.c_int),
         "lbm_last_error": ([vp], C.c_char_p),
         "lbm_set_flag": ([vp, vp], C.c_int),
+        "lbm_set_flag_slab": ([vp, vp, i32, i32], C.c_int),
         "lbm_geo_pre": ([vp], C.c_int),
         "lbm_index_transform": ([vp, P(i64)], C.c_int),
         "lbm_local_stored_count": ([vp, P(i64)], C.c_int),
@@ -191,6 +192,19 @@ class Case:
         if flag.shape != (d.nz, d.ny, d.nx):
             raise ValueError(f"flag shape {flag.shape} != {(d.nz, d.ny, d.nx)}")
         self._ck(self._L.lbm_set_flag(self._h, flag.ctypes.data))
+
+    def set_flag_slab(self, flag: np.ndarray, z_first: int):
+        """planes [z_first, z_first + len(flag)) of the voxel field, uint8 [z][y][x]"""
+        d = self.desc
+        flag = np.ascontiguousarray(flag, dtype=np.uint8)
+        if flag.shape[1:] != (d.ny, d.nx):
+            raise ValueError(f"flag slab shape {flag.shape} does not match ny, nx = {(d.ny, d.nx)}")
+        self._ck(self._L.lbm_set_flag_slab(self._h, flag.ctypes.data, int(z_first), int(flag.shape[0])))
+
+    def needed_flag_planes(self):
+        """z range of the voxel field this (slab) handle reads in geo_pre"""
+        d = self.desc
+        return max(0, d.z_begin - 3), min(d.nz, d.z_end + 3)
 
     def geo_pre(self):
         self._ck(self._L.lbm_geo_pre(self._h))

@@ -38,6 +38,7 @@ struct SolverBase {
     std::string err;
     lbm_case_desc d{};
     virtual int set_flag(const int32_t *flag) = 0;
+    virtual int set_flag_slab(const uint8_t *flag, int z_first, int z_count) = 0;
     virtual int geo_pre() = 0;
     virtual int index_transform(int64_t *nlat) = 0;
     virtual int local_stored_count(int64_t *n) = 0;
@@ -95,6 +96,8 @@ struct Solver final : SolverBase {
     int step_flags = 0;
     // host
     std::vector<int32_t> h_flag;  // global Cartesian, optional
+    std::vector<uint8_t> h_flag_slab;  // planes [slab_z0, slab_z0 + slab_nz) only, optional
+    int slab_z0 = 0, slab_nz = 0;
     std::vector<float> h_in, h_out;
     // device
     uint8_t *d_flag = nullptr;
@@ -192,6 +195,19 @@ struct Solver final : SolverBase {
     int set_flag(const int32_t *flag) override {
         if (!flag) FAIL(LBM_ERR_ARG, "null flag");
         h_flag.assign(flag, flag + (size_t)d.nx * d.ny * d.nz);
+        h_flag_slab.clear();
+        have_flag = true;
+        return 0;
+    }
+
+    int set_flag_slab(const uint8_t *flag, int z_first, int z_count) override {
+        if (!flag || z_count <= 0) FAIL(LBM_ERR_ARG, "null / empty flag slab");
+        if (z_first > ext.z0 || z_first + z_count < ext.z1)
+            FAIL(LBM_ERR_ARG, "flag slab [%d,%d) does not cover the planes [%d,%d) this handle needs", z_first,
+                 z_first + z_count, ext.z0, ext.z1);
+        h_flag_slab.assign(flag, flag + (size_t)d.nx * d.ny * z_count);
+        slab_z0 = z_first, slab_nz = z_count;
+        h_flag.clear();
         have_flag = true;
         return 0;
     }
@@ -235,9 +251,13 @@ struct Solver final : SolverBase {
             std::vector<uint8_t> tmp((size_t)ext.cells(), 0);
             for (int z = ext.z0; z < ext.z1; z++)
                 for (int y = 0; y < d.ny; y++) {
-                    const int32_t *srow = &h_flag[(size_t)d.nx * ((size_t)y + (size_t)d.ny * z)];
                     uint8_t *drow = &tmp[(size_t)ext.px * ((size_t)y + (size_t)d.ny * (z - ext.z0))];
-                    for (int x = 0; x < d.nx; x++) drow[x] = (uint8_t)srow[x];
+                    if (!h_flag_slab.empty()) {
+                        memcpy(drow, &h_flag_slab[(size_t)d.nx * ((size_t)y + (size_t)d.ny * (z - slab_z0))], (size_t)d.nx);
+                    } else {
+                        const int32_t *srow = &h_flag[(size_t)d.nx * ((size_t)y + (size_t)d.ny * z)];
+                        for (int x = 0; x < d.nx; x++) drow[x] = (uint8_t)srow[x];
+                    }
                 }
             CK(cudaMemcpyAsync(d_flag, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, st));
             CK(cudaStreamSynchronize(st));
@@ -1109,6 +1129,7 @@ const char *lbm_last_error(lbm_handle h) { return h ? h->s->err.c_str() : lbm::g
     if (!h) return LBM_ERR_ARG
 
 int lbm_set_flag(lbm_handle h, const int32_t *f) { H_OR_FAIL; return h->s->set_flag(f); }
+int lbm_set_flag_slab(lbm_handle h, const uint8_t *f, int32_t z0, int32_t nz) { H_OR_FAIL; return h->s->set_flag_slab(f, z0, nz); }
 int lbm_geo_pre(lbm_handle h) { H_OR_FAIL; return h->s->geo_pre(); }
 int lbm_index_transform(lbm_handle h, int64_t *n) { H_OR_FAIL; return h->s->index_transform(n); }
 int lbm_local_stored_count(lbm_handle h, int64_t *n) { H_OR_FAIL; return n ? h->s->local_stored_count(n) : LBM_ERR_ARG; }

@@ -84,13 +84,15 @@ class SlabCase(api.Case):
         self.world = dist.get_world_size(group)
         self._bufs = None
 
-    def setup(self, flag=None, bc_planes=None):
+    def setup(self, flag=None, bc_planes=None, flag_slab=None):
         """geo_pre -> (all-gather of stored counts) -> index_transform -> read_vel -> initialize"""
         import torch
         import torch.distributed as dist
 
         if flag is not None:
             self.set_flag(flag)
+        if flag_slab is not None:  # only the planes this rank needs: (uint8 array, z_first)
+            self.set_flag_slab(*flag_slab)
         self.geo_pre()
         mine = torch.tensor([self.local_stored_count()], dtype=torch.int64, device="cuda")
         allc = [torch.zeros_like(mine) for _ in range(self.world)]

@@ -19,7 +19,7 @@ def test_nccl_slabs_equal_single_domain():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    world = 4 if n >= 4 else 2
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]

@@ -107,3 +107,27 @@ def test_pulsatile_slabs():
     cs, _ = run_slabs("bif", None, 2, 40, L.F64, L.MATH_FAST, pulse=pulse)
     for k in range(4):
         assert np.array_equal(np.concatenate([c.get_fields()[k] for c in cs]), ref[k])
+
+
+def test_per_slab_masks():
+    """each slab is handed only the planes of the voxel field it needs (lbm_set_flag_slab)"""
+    import lattice_boltzmann_method_gpu_b200 as L
+    from lattice_boltzmann_method_gpu_b200 import slab
+
+    flag = H.bif_flag()
+    one = H.gpu_case("bif", None, L.F64, L.MATH_FAST, storage=L.STORE_SPARSE_AB)
+    nlat = H.gpu_setup(one, "bif")
+    one.step(15)
+    ref = one.get_fields()
+    cs = []
+    for r in slab.slab_ranges(32, 3):
+        c = H.gpu_case("bif", None, L.F64, L.MATH_FAST, z_range=r, storage=L.STORE_SPARSE_AB)
+        z0, z1 = c.needed_flag_planes()
+        c.set_flag_slab(flag[z0:z1].astype(np.uint8), z0)
+        with pytest.raises(L.LbmError):
+            c.set_flag_slab(flag[z0 + 1:z1].astype(np.uint8), z0 + 1)  # does not cover the needed planes
+        c.geo_pre()
+        cs.append(c)
+    offs, total = slab.compact_offsets([c.local_stored_count() for c in cs])
+    assert total == nlat
+    assert np.array_equal(np.concatenate([c.get_geo() for c in cs]), one.get_geo())
