@@ -200,7 +200,7 @@ def workload_config(args, world):
     return {"workload": f"dense lid-driven cavity {gx}x{gy}x{gz} D3Q19 BGK {args.precision}, tau=0.55, Re~222 (ldc.cu rules), "
                         f"z-slabs of {gz // world} planes per GPU",
             "storage": args.storage, "math": "fast", "bytes_per_node_update": BYTES_PER_LU[args.precision],
-            "parallelism": f"zslab{world}", "l2_policy": "working set (>=20 GB) far exceeds the 126 MB L2; no flush needed"}
+            "parallelism": f"zslab{world}", "halo_exchange": args.halo if world > 1 else None, "l2_policy": "working set (>=20 GB) far exceeds the 126 MB L2; no flush needed"}
 
 
 def run_ours(args):
@@ -235,6 +235,8 @@ def run_ours(args):
     def setup(c):
         if world > 1:
             c.setup()
+            if args.halo == "p2p":
+                c.enable_p2p()
         else:
             c.geo_pre()
             c.index_transform()
@@ -360,6 +362,8 @@ def main():
     ap.add_argument("--storage", default="ab", choices=["ab", "aa"])
     ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
                     help="global box (default n x n x n*gpus, i.e. weak scaling with one n^3 slab per GPU)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU halo exchange: peer stores fused into the step kernel, or pack + NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128)

@@ -239,6 +239,25 @@ int lbm_step_interior(lbm_handle h);
 int lbm_step_end(lbm_handle h);
 /* S of the most recent step run with LBM_STEP_VELSUM (this slab's share) */
 int lbm_last_velsum(lbm_handle h, double *value);
+/* ---- fused peer-to-peer halo exchange ----
+ * Instead of pack -> transport -> unpack, the step kernel itself stores the 5 crossing populations of
+ * every FLUID node of a face plane straight into the neighbouring slab's halo plane (device memory of
+ * another GPU mapped over NVLink, or of another handle on the same GPU).  Only fluid threads exist,
+ * so solid halo slots are never clobbered and no unpack mask is needed.  The caller still has to
+ * order the steps: a slab may start step t+1 only after both neighbours finished step t.
+ *   lbm_p2p_export: IPC handles + raw pointers of the two population buffers, their q stride, and the
+ *                   cell/compact offset of this slab's low and high halo planes;
+ *   lbm_p2p_open / lbm_p2p_close: map / unmap another process's buffer (cudaIpcOpenMemHandle);
+ *   lbm_p2p_attach: side 0/1 now pushes into the neighbour's buffers (peer_a/peer_b in the same order
+ *                   as exported) at peer_halo_c0 = the neighbour's halo-plane offset facing this slab. */
+typedef struct {
+    unsigned char bytes[64];
+} lbm_ipc_handle;
+int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t *qstride, int64_t halo_c0[2]);
+int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr);
+int lbm_p2p_close(void *dev_ptr);
+int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64_t peer_qstride, int64_t peer_halo_c0);
+
 /* cudaStream_t of the handle as an opaque pointer (for event / NCCL interop) */
 void *lbm_stream(lbm_handle h);
 int lbm_sync(lbm_handle h);

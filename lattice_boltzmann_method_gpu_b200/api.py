@@ -77,6 +77,7 @@ ABI_SYMBOLS = [
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
     "lbm_device_bytes", "lbm_output_save", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
+    "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach",
 ]
 
 _lib = None
@@ -127,6 +128,10 @@ def load_library() -> C.CDLL:
         "lbm_step_interior": ([vp], C.c_int),
         "lbm_step_end": ([vp], C.c_int),
         "lbm_last_velsum": ([vp, P(dbl)], C.c_int),
+        "lbm_p2p_export": ([vp, vp, P(vp), P(i64), P(i64)], C.c_int),
+        "lbm_p2p_open": ([vp, P(vp)], C.c_int),
+        "lbm_p2p_close": ([vp], C.c_int),
+        "lbm_p2p_attach": ([vp, i32, vp, vp, i64, i64], C.c_int),
         "lbm_stream": ([vp], vp),
         "lbm_sync": ([vp], C.c_int),
     }
@@ -267,6 +272,20 @@ class Case:
         self._ck(self._L.lbm_halo_buffers(self._h, side, C.byref(s), C.byref(r), C.byref(ns), C.byref(nr)))
         return s.value, r.value, ns.value, nr.value
 
+    # -- fused peer-to-peer halo exchange
+    def p2p_export(self):
+        """(two 64-byte IPC handles, two raw device pointers, q stride, [low, high] halo-plane offsets)"""
+        handles = (C.c_ubyte * 128)()
+        ptrs = (C.c_void_p * 2)()
+        qs = C.c_int64()
+        c0 = (C.c_int64 * 2)()
+        self._ck(self._L.lbm_p2p_export(self._h, handles, ptrs, C.byref(qs), c0))
+        raw = bytes(handles)
+        return [raw[:64], raw[64:]], [ptrs[0], ptrs[1]], qs.value, [c0[0], c0[1]]
+
+    def p2p_attach(self, side: int, peer_a: int, peer_b: int, peer_qstride: int, peer_halo_c0: int):
+        self._ck(self._L.lbm_p2p_attach(self._h, side, peer_a, peer_b, peer_qstride, peer_halo_c0))
+
     def residual(self, kind: int = RES_VELSUM) -> float:
         v = C.c_double()
         self._ck(self._L.lbm_residual(self._h, kind, C.byref(v)))
@@ -335,6 +354,17 @@ class Case:
     @property
     def stream(self) -> int:
         return self._L.lbm_stream(self._h)
+
+
+def p2p_open(handle_bytes: bytes) -> int:
+    """map a population buffer exported by another process (cudaIpcOpenMemHandle)"""
+    L = load_library()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
+    ptr = C.c_void_p()
+    rc = L.lbm_p2p_open(buf, C.byref(ptr))
+    if rc:
+        raise LbmError(rc, L.lbm_last_error(None).decode())
+    return ptr.value
 
 
 def make_case(case_rule: int, *, n=None, dims=None, precision=F32, math_mode=MATH_FAST, storage=STORE_DENSE_AB,

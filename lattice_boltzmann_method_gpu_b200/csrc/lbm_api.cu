@@ -60,6 +60,8 @@ struct SolverBase {
     virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
+    virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) = 0;
+    virtual int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) = 0;
     virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
     virtual int sync() = 0;
     virtual void *stream_ptr() = 0;
@@ -119,6 +121,9 @@ struct Solver final : SolverBase {
     double last_S = 0.0;
     long long pend_i0 = 0, pend_i1 = 0;
     bool interior_pending = false;
+    // fused peer-to-peer halo exchange (per side: neighbour's two buffers, q stride, halo offset)
+    T *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    long long peer_qs[2] = {0, 0}, peer_c0[2] = {0, 0};
     // sparse storage (reference compact order + run segments)
     bool sparse = false;
     long long n_lo_stored = 0, stored_box = 0;   // stored nodes of the low halo plane / of the whole state box
@@ -549,9 +554,19 @@ struct Solver final : SolverBase {
         p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
         return p;
     }
-    int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc) {
+    int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc, int face_sides = 0) {
         if (c1 <= c0) return 0;
         StepParams<T> p = make_params(c0, c1, acc);
+        // face_sides bit 0: this range is the lowest owned plane, bit 1: the highest -> push to attached peers
+        const int which = d_nxt == d_fa ? 0 : 1;
+        if ((face_sides & 2) && peer_buf[1][which]) {
+            p.peer_up = peer_buf[1][which], p.peer_up_qs = peer_qs[1], p.peer_up_c0 = peer_c0[1];
+            p.face_c0 = sparse ? face_id0[1] : c0;
+        }
+        if ((face_sides & 1) && peer_buf[0][which]) {
+            p.peer_dn = peer_buf[0][which], p.peer_dn_qs = peer_qs[0], p.peer_dn_c0 = peer_c0[0];
+            p.face_c0 = sparse ? face_id0[0] : c0;
+        }
         if (sparse) {
             SparseParams<T> sp{};
             sp.base = p, sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc;
@@ -606,17 +621,20 @@ struct Solver final : SolverBase {
         const int zt = own_z1 - 1, zb = own_z0;
         long long i0 = plane_c(own_z0), i1 = plane_c(own_z1);
         if (hi_halo) {
-            if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, d_acc))) return r;
-            if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[1], face_n[1], 1, d_send[1], face_n[1], st));
-            else CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
-            launches++;
+            const int sides = 2 | ((lo_halo && zb == zt) ? 1 : 0);
+            if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, d_acc, sides))) return r;
+            if (!peer_buf[1][0]) {
+                if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[1], face_n[1], 1, d_send[1], face_n[1], st));
+                else CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
+                launches++;
+            }
             i1 = plane_c(zt);
         }
         if (lo_halo && !(hi_halo && zb == zt)) {
-            if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, d_acc))) return r;
+            if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, d_acc, 1))) return r;
             i0 = plane_c(zb + 1);
         }
-        if (lo_halo) {
+        if (lo_halo && !peer_buf[0][0]) {
             if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[0], face_n[0], 0, d_send[0], face_n[0], st));
             else CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
             launches++;
@@ -641,12 +659,12 @@ struct Solver final : SolverBase {
             int r = step_interior();
             if (r) return r;
         }
-        if (lo_halo) {
+        if (lo_halo && !peer_buf[0][0]) {
             if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[0], halo_n[0], 0, d_recv[0], halo_n[0], st));
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
             launches++;
         }
-        if (hi_halo) {
+        if (hi_halo && !peer_buf[1][0]) {
             if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[1], halo_n[1], 1, d_recv[1], halo_n[1], st));
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
             launches++;
@@ -663,6 +681,37 @@ struct Solver final : SolverBase {
     }
     int last_velsum(double *v) override {
         *v = last_S;
+        return 0;
+    }
+    int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "p2p_export before initialize");
+        if (d.storage == LBM_STORE_DENSE_AA) FAIL(LBM_ERR_ARG, "in-place storage has no slab support");
+        CK(cudaSetDevice(d.device));
+        static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(lbm_ipc_handle), "handle size");
+        T *bufs[2] = {d_fa, d_fb};
+        for (int k = 0; k < 2; k++) {
+            if (h2) {
+                cudaIpcMemHandle_t ih;
+                CK(cudaIpcGetMemHandle(&ih, bufs[k]));
+                memset(&h2[k], 0, sizeof(lbm_ipc_handle));
+                memcpy(&h2[k], &ih, sizeof ih);
+            }
+            if (ptrs) ptrs[k] = bufs[k];
+        }
+        if (qs) *qs = qstride;
+        if (halo_c0) {
+            halo_c0[0] = sparse ? halo_id0[0] : 0;
+            halo_c0[1] = sparse ? halo_id0[1] : (long long)(box.z1 - box.z0 - 1) * box.plane;
+        }
+        return 0;
+    }
+    int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) override {
+        if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
+        if (!have_init) FAIL(LBM_ERR_STATE, "p2p_attach before initialize");
+        if (!(side == 0 ? lo_halo : hi_halo)) FAIL(LBM_ERR_ARG, "no neighbour on side %d", side);
+        if ((pa == nullptr) != (pb == nullptr)) FAIL(LBM_ERR_ARG, "both peer buffers or none");
+        peer_buf[side][0] = (T *)pa, peer_buf[side][1] = (T *)pb;
+        peer_qs[side] = pqs, peer_c0[side] = pc0;
         return 0;
     }
     int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) override {
@@ -1161,6 +1210,26 @@ int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max,
 int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) {
     H_OR_FAIL;
     return h->s->halo_buffers(side, send, recv, send_bytes, recv_bytes);
+}
+int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t *qstride, int64_t halo_c0[2]) {
+    H_OR_FAIL;
+    return h->s->p2p_export(handles, ptrs, qstride, halo_c0);
+}
+int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr) {
+    if (!handle || !dev_ptr) return LBM_ERR_ARG;
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handle, sizeof ih);
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, ih, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        lbm::g_create_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        return LBM_ERR_CUDA;
+    }
+    return LBM_OK;
+}
+int lbm_p2p_close(void *dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? LBM_OK : LBM_ERR_CUDA; }
+int lbm_p2p_attach(lbm_handle h, int32_t side, void *pa, void *pb, int64_t pqs, int64_t pc0) {
+    H_OR_FAIL;
+    return h->s->p2p_attach(side, pa, pb, pqs, pc0);
 }
 int lbm_step_begin(lbm_handle h, int32_t flags) { H_OR_FAIL; return h->s->step_begin(flags); }
 int lbm_step_interior(lbm_handle h) { H_OR_FAIL; return h->s->step_interior(); }

@@ -70,6 +70,12 @@ struct StepParams {
     const T *plane_in, *plane_out;  // nx * nz(global) each
     int parity;                     // AA: 0 even (local) step, 1 odd (shifted) step
     int speculative;                // issue the population loads before the segment class is known
+    // fused halo exchange: when this launch covers a face plane, fluid threads also store their
+    // upward (c_z=+1) / downward (c_z=-1) populations into the neighbour slab's halo plane
+    T *peer_up, *peer_dn;           // neighbour's destination buffer (peer / same-device memory) or null
+    long long peer_up_qs, peer_dn_qs;   // its q stride
+    long long peer_up_c0, peer_dn_c0;   // offset of its halo plane (cells, or compact ids for sparse)
+    long long face_c0;              // offset of this launch's plane (cell of c_begin / first compact id)
     int case_rule;                  // lbm_case_rule (initial-state rule, for static links in the AA odd step)
     T u_init;                       // lbm_case_desc.u_max
 };

@@ -201,6 +201,22 @@ __device__ __forceinline__ long long slot_index(int q, long long c, long long qs
 
 // collide, store, moments, boundary links of one fluid cell whose post-streaming
 // populations are already in f[]
+// Fused halo exchange: the populations that leave through a z face go straight into the neighbour
+// slab's halo plane (same x,y; `i` = offset inside the plane).  c_z=+1: q in {5,11,13,15,16}.
+template <typename T>
+__device__ __forceinline__ void push_to_peers(const StepParams<T> &p, long long i, const T (&f)[Q]) {
+    if (p.peer_up) {
+        T *d = p.peer_up + p.peer_up_c0 + i;
+        d[5 * p.peer_up_qs] = f[5], d[11 * p.peer_up_qs] = f[11], d[13 * p.peer_up_qs] = f[13];
+        d[15 * p.peer_up_qs] = f[15], d[16 * p.peer_up_qs] = f[16];
+    }
+    if (p.peer_dn) {
+        T *d = p.peer_dn + p.peer_dn_c0 + i;
+        d[6 * p.peer_dn_qs] = f[6], d[12 * p.peer_dn_qs] = f[12], d[14 * p.peer_dn_qs] = f[14];
+        d[17 * p.peer_dn_qs] = f[17], d[18 * p.peer_dn_qs] = f[18];
+    }
+}
+
 // WALL_READY: the caller already holds the node's wall mask in `wallw`; otherwise it is fetched here,
 // lazily, by the few nodes that need it
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, int MODE, bool WALL_READY>
@@ -224,6 +240,7 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
         p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
     }
     if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
+    if (MODE == MODE_AB && (p.peer_up || p.peer_dn)) push_to_peers<T>(p, c - p.face_c0, f);
     if (node & NODE_LINKS) {
         // wall links: half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
         const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (WALL_READY ? wallw : p.wall[c]);

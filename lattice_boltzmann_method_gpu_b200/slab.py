@@ -83,6 +83,8 @@ class SlabCase(api.Case):
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._bufs = None
+        self._p2p = False
+        self._tick = None
 
     def setup(self, flag=None, bc_planes=None, flag_slab=None):
         """geo_pre -> (all-gather of stored counts) -> index_transform -> read_vel -> initialize"""
@@ -105,6 +107,26 @@ class SlabCase(api.Case):
         self.initialize()
         self._wrap_buffers()
 
+    def enable_p2p(self):
+        """Fused halo exchange: every rank maps its neighbours' population buffers (CUDA IPC over
+        NVLink) and the step kernel stores the crossing populations there itself; what is left of the
+        transport is one tiny all-reduce per step that keeps the slabs in lock-step."""
+        import torch
+        import torch.distributed as dist
+
+        handles, _, qs, c0 = self.p2p_export()
+        mine = {"handles": handles, "qs": qs, "c0": c0}
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= nb < self.world:
+                pa, pb = (api.p2p_open(h) for h in everyone[nb]["handles"])
+                # my low face feeds the neighbour's HIGH halo plane and vice versa
+                self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["c0"][1 - side])
+        self._tick = torch.zeros(1, device="cuda")
+        self._p2p = True
+        dist.barrier(group=self.group)
+
     def _wrap_buffers(self):
         import torch
 
@@ -122,6 +144,15 @@ class SlabCase(api.Case):
     def _one_step(self, flags=0):
         import torch
 
+        if self._p2p:
+            import torch.distributed as dist
+
+            self.step_begin(flags)  # face planes first: their peer stores start crossing NVLink ...
+            self.step_interior()    # ... while the interior planes are updated
+            self.step_end()
+            with torch.cuda.stream(self._ext):  # in-stream barrier: nobody starts t+1 before all finished t
+                dist.all_reduce(self._tick, group=self.group)
+            return
         self.step_begin(flags)  # face planes + pack, queued on the library's stream
         (s_lo, r_lo), (s_hi, r_hi) = self._bufs
         # torch.distributed orders NCCL's stream after what `self._ext` holds so far (faces + pack)

@@ -131,3 +131,48 @@ def test_per_slab_masks():
     offs, total = slab.compact_offsets([c.local_stored_count() for c in cs])
     assert total == nlat
     assert np.array_equal(np.concatenate([c.get_geo() for c in cs]), one.get_geo())
+
+
+@pytest.mark.parametrize("name,n,P,storage_name", [("ldc", 24, 3, "dense"), ("bif", None, 4, "dense"), ("bif", None, 4, "sparse"),
+                                                   ("cor", None, 3, "sparse"), ("ldc", 12, 12, "dense")])
+def test_fused_peer_store_halo_exchange(name, n, P, storage_name):
+    """lbm_p2p_attach: the step kernel stores the crossing populations straight into the neighbouring
+    handle's halo plane (here: another handle on the same GPU); no pack / unpack / copy at all"""
+    import lattice_boltzmann_method_gpu_b200 as L
+    from lattice_boltzmann_method_gpu_b200 import slab
+
+    storage = L.STORE_SPARSE_AB if storage_name == "sparse" else L.STORE_DENSE_AB
+    steps = 21
+    one = H.gpu_case(name, n, L.F64, L.MATH_FAST, storage=storage)
+    H.gpu_setup(one, name)
+    one.step(steps)
+    ref = one.get_fields()
+    nz = {"ldc": n, "pos": n, "bif": 32, "cor": 44}[name]
+    cs = [H.gpu_case(name, n, L.F64, L.MATH_FAST, z_range=r, storage=storage) for r in slab.slab_ranges(nz, P)]
+    for c in cs:
+        c.geo_pre()
+    offs, total = slab.compact_offsets([c.local_stored_count() for c in cs])
+    for c, o in zip(cs, offs):
+        c.set_compact_offset(o, total)
+        c.index_transform()
+        if name == "bif":
+            c.set_bc_planes(*H.bif_bc_planes())
+        c.initialize()
+    exp = [c.p2p_export() for c in cs]
+    for r, c in enumerate(cs):
+        for side, nb in ((0, r - 1), (1, r + 1)):
+            if 0 <= nb < P:
+                _, ptrs, qs, c0 = exp[nb]
+                c.p2p_attach(side, ptrs[0], ptrs[1], qs, c0[1 - side])
+    launches0 = sum(c.launch_count for c in cs)
+    for it in range(steps):
+        for c in cs:
+            c.step_begin(L.STEP_MOMENTS if it == steps - 1 else 0)
+            c.step_interior()
+            c.step_end()
+        for c in cs:
+            c.sync()  # lock-step
+    for k in range(4):
+        assert np.array_equal(np.concatenate([c.get_fields()[k] for c in cs]), ref[k]), f"field {k}"
+    # only step kernels ran: at most face(s) + interior per slab and step
+    assert sum(c.launch_count for c in cs) - launches0 <= 3 * P * steps + 4 * P

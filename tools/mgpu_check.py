@@ -28,13 +28,16 @@ def main():
     for name, n, steps in (("ldc", 40, 60), ("bif", None, 80), ("cor", None, 50), ("pos", 32, 40)):
         nz = {"ldc": n, "pos": n, "bif": 32, "cor": 44}[name]
         z0, z1 = slab.slab_ranges(nz, world)[rank]
-        base = H.gpu_case(name, n, L.F64, L.MATH_FAST, z_range=(z0, z1))
+        storage = L.STORE_SPARSE_AB if os.environ.get("LBM_SPARSE") == "1" else L.STORE_DENSE_AB
+        base = H.gpu_case(name, n, L.F64, L.MATH_FAST, z_range=(z0, z1), storage=storage)
         d = base.desc
         d.device = local
         base.close()
         c = slab.SlabCase(d)
         flag = H.bif_flag() if name == "bif" else (H.synthetic_openings_mask()[0] if name == "cor" else None)
         c.setup(flag=flag, bc_planes=H.bif_bc_planes() if name == "bif" else None)
+        if os.environ.get("LBM_P2P") == "1":
+            c.enable_p2p()
         c.step(steps)
         mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
         counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
@@ -48,7 +51,7 @@ def main():
                 bufs[rank] = mine[k]
             gathered.append(torch.cat(bufs).cpu().numpy())
         if rank == 0:
-            one = H.gpu_case(name, n, L.F64, L.MATH_FAST)
+            one = H.gpu_case(name, n, L.F64, L.MATH_FAST, storage=storage)
             H.gpu_setup(one, name)
             one.step(steps)
             ref = one.get_fields()
