@@ -125,6 +125,31 @@ __device__ __forceinline__ void feq_all_ldc_init(T rho, T ux, T uy, T uz, T *feq
     feq[18] = rho * w2 * (T(1.0) - T(3.0) * (uy + uz) + T(4.5) * (yz2 + yz) - T(1.5) * u2);
 }
 
+// r / d for d in {3, 18} without a division: with hi + lo = 1/d to twice the working precision,
+//   p = r*hi,  e = fma(r, hi, -p) (the exact rounding error of p),  result = p + (e + r*lo)
+// is r/d rounded once (up to rare ties) -- 4 dependent instructions instead of ~10 / ~25.
+// (Adding r*lo to the ROUNDED p alone changes nothing: lo is below half an ulp of hi.)
+template <typename T>
+__device__ __forceinline__ T div_by_const(T r, T hi, T lo) {
+    const T p = r * hi;
+    return p + fma(r, lo, fma(r, hi, -p));
+}
+template <typename T>
+__device__ __forceinline__ T rho_over(T r, int d);
+template <>
+__device__ __forceinline__ float rho_over<float>(float r, int d) {
+    constexpr float h3 = (float)(1.0 / 3.0), l3 = (float)(1.0 / 3.0 - (double)h3);
+    constexpr float h18 = (float)(1.0 / 18.0), l18 = (float)(1.0 / 18.0 - (double)h18);
+    return d == 3 ? div_by_const<float>(r, h3, l3) : div_by_const<float>(r, h18, l18);
+}
+template <>
+__device__ __forceinline__ double rho_over<double>(double r, int d) {
+    // 1/3 - fl(1/3) and 1/18 - fl(1/18), exact to double precision
+    constexpr double h3 = 0x1.5555555555555p-2, l3 = 0x1.5555555555555p-56;
+    constexpr double h18 = 0x1.c71c71c71c71cp-5, l18 = 0x1.c71c71c71c71cp-59;
+    return d == 3 ? div_by_const<double>(r, h3, l3) : div_by_const<double>(r, h18, l18);
+}
+
 // ---------------------------------------------------------------------------
 // moments + BGK collision of one node.  f[] in: post-streaming populations,
 // out: post-collision.  Moments returned are the pre-collision ones the
@@ -165,10 +190,12 @@ __device__ __forceinline__ void collide_bgk(T (&f)[Q], T tau, T inv_tau, T &rho,
         const T om = inv_tau;
         // feq_q = rho w_q (1 + 3cu + 4.5cu^2 - 1.5u^2)
         const T base = T(1.0) - T(1.5) * (ux * ux + uy * uy + uz * uz);
-        // rho w_q by correctly rounded DIVISION, as the reference does (rho/3, rho/18, rho/36):
-        // multiplying by a rounded 1/18 gives every cell the same signed error in sum_q feq_q,
-        // i.e. a coherent mass drift of ~2 ulp per step -- visible in fp32 after 1000 steps
-        const T k0 = r / T(3.0), k1 = r / T(18.0), k2 = T(0.5) * k1;
+        // rho w_q must not carry a systematic error: multiplying by a rounded 1/18 gives every cell
+        // the same signed error in sum_q feq_q, i.e. a coherent mass drift of ~2 ulp per step
+        // (visible in fp32 after 1000 steps; the reference divides, rho/18).  A division costs
+        // ~10 (fp32) / ~25 (fp64) dependent instructions on a latency-bound kernel, so the weight is
+        // applied as an error-free two-term product instead (rho_over).
+        const T k0 = rho_over<T>(r, 3), k1 = rho_over<T>(r, 18), k2 = T(0.5) * k1;
         f[0] = f[0] + om * (k0 * base - f[0]);
 #define LBM_PAIR(qp, qm, cu, kw)                                    \
     {                                                               \

@@ -127,6 +127,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_step_v2(const double *__restric
     for (int q = 0; q < Q; q++) *reinterpret_cast<double2 *>(dst + q * p.qs + c) = make_double2(f0[q], f1[q]);
 }
 
+// ---- two rows per thread: cells c and c + px, scalar coalesced accesses, 38 loads in flight per thread
+template <typename T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_step_2rows(const T *__restrict__ src, T *__restrict__ dst, P p, T inv_tau) {
+    // block covers BLOCK consecutive cells of row pair (2r, 2r+1)
+    const long long per_pair = 2LL * p.px;
+    const long long idx = (long long)blockIdx.x * BLOCK + threadIdx.x;  // index among first-row cells
+    const long long pair = idx / p.px, x = idx - pair * p.px;
+    const long long c = p.c0 + pair * per_pair + x;
+    if (c + p.px >= p.c1) return;
+    T f0[Q], f1[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const T *a = src + q * p.qs + c - (cxq(q) + (long long)p.px * cyq(q) + p.plane * czq(q));
+        f0[q] = __ldg(a);
+        f1[q] = __ldg(a + p.px);
+    }
+    collide<T>(f0, inv_tau);
+    collide<T>(f1, inv_tau);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        dst[q * p.qs + c] = f0[q];
+        dst[q * p.qs + c + p.px] = f1[q];
+    }
+}
+
 // ---- AA pattern: even step (purely local, aligned) and odd step (shifted reads AND writes), in place
 template <typename T, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_aa_even(T *__restrict__ f_, P p, T inv_tau) {
@@ -221,6 +246,15 @@ void run(int N, long long qpad) {
         unsigned gv = (unsigned)((n / 2 + 127) / 128);
         rep("step 2 nodes/thread 128-bit b128 minb2", time_it([&](int i) { if (i & 1) k_step_v2<128, 2><<<gv, 128>>>((const double *)b, (double *)a, p, it); else k_step_v2<128, 2><<<gv, 128>>>((const double *)a, (double *)b, p, it); }));
         rep("step 2 nodes/thread 128-bit b128 minb3", time_it([&](int i) { if (i & 1) k_step_v2<128, 3><<<gv, 128>>>((const double *)b, (double *)a, p, it); else k_step_v2<128, 3><<<gv, 128>>>((const double *)a, (double *)b, p, it); }));
+    }
+    {
+        unsigned g2 = (unsigned)((n / 2 + 127) / 128), g2b = (unsigned)((n / 2 + 255) / 256);
+        rep("step 2 rows/thread b128 minb3", time_it([&](int i) { if (i & 1) k_step_2rows<T, 128, 3><<<g2, 128>>>(b, a, p, it); else k_step_2rows<T, 128, 3><<<g2, 128>>>(a, b, p, it); }));
+        rep("step 2 rows/thread b128 minb4", time_it([&](int i) { if (i & 1) k_step_2rows<T, 128, 4><<<g2, 128>>>(b, a, p, it); else k_step_2rows<T, 128, 4><<<g2, 128>>>(a, b, p, it); }));
+        rep("step 2 rows/thread b128 minb6", time_it([&](int i) { if (i & 1) k_step_2rows<T, 128, 6><<<g2, 128>>>(b, a, p, it); else k_step_2rows<T, 128, 6><<<g2, 128>>>(a, b, p, it); }));
+        rep("step 2 rows/thread b256 minb2", time_it([&](int i) { if (i & 1) k_step_2rows<T, 256, 2><<<g2b, 256>>>(b, a, p, it); else k_step_2rows<T, 256, 2><<<g2b, 256>>>(a, b, p, it); }));
+        STEP("step b128 minb8 ldg", 128, 8, 1, false, g128)
+        STEP("step b128 minb10 ldg", 128, 10, 1, false, g128)
     }
     rep("AA even (local rd/wr, in place)", time_it([&](int) { k_aa_even<T, 256, 2><<<g256, 256>>>(a, p, it); }));
     rep("AA odd (shifted rd + shifted wr, in place)", time_it([&](int) { k_aa_odd<T, 256, 2><<<g256, 256>>>(a, p, it); }));
