@@ -218,6 +218,14 @@ int lbm_run_fixed(lbm_handle h, int32_t repeat, int32_t time_save, int32_t write
 int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max, int32_t time_save,
                      int32_t write_files, int32_t *iterations, double *residual);
 
+/* ---- checkpoint / restart (the reference has none: its periodic VTK is output only) ----
+ * Binary dump of the population buffer(s) this handle needs to continue, the step counter and a
+ * header that pins case rule, dims, slab range, precision and storage; lbm_checkpoint_load restores
+ * a handle that was set up (geo_pre .. initialize) for the same case.  A restarted run continues
+ * bit-identically. */
+int lbm_checkpoint_save(lbm_handle h, const char *path);
+int lbm_checkpoint_load(lbm_handle h, const char *path);
+
 /* ---- z-slab halo exchange: the 5 populations crossing each face ----
  * side 0 = low-z face (sends q with c_z=-1, receives c_z=+1), side 1 = high-z.
  * lbm_halo_buffers returns DEVICE pointers to the contiguous send / receive

@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
     "lbm_device_bytes", "lbm_output_save", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
-    "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach",
+    "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
 ]
 
 _lib = None
@@ -132,6 +132,8 @@ def load_library() -> C.CDLL:
         "lbm_p2p_open": ([vp, P(vp)], C.c_int),
         "lbm_p2p_close": ([vp], C.c_int),
         "lbm_p2p_attach": ([vp, i32, vp, vp, i64, i64], C.c_int),
+        "lbm_checkpoint_save": ([vp, C.c_char_p], C.c_int),
+        "lbm_checkpoint_load": ([vp, C.c_char_p], C.c_int),
         "lbm_stream": ([vp], vp),
         "lbm_sync": ([vp], C.c_int),
     }
@@ -331,6 +333,12 @@ class Case:
         self._ck(self._L.lbm_run_converge(self._h, max_it, tol, stag_max, time_save, int(write_files),
                                           C.byref(its), C.byref(res)))
         return its.value, res.value
+
+    def checkpoint_save(self, path):
+        self._ck(self._L.lbm_checkpoint_save(self._h, os.fsencode(str(path))))
+
+    def checkpoint_load(self, path):
+        self._ck(self._L.lbm_checkpoint_load(self._h, os.fsencode(str(path))))
 
     def sync(self):
         self._ck(self._L.lbm_sync(self._h))

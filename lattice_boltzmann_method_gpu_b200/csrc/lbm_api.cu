@@ -60,6 +60,7 @@ struct SolverBase {
     virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
+    virtual int checkpoint(const char *path, bool save) = 0;
     virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) = 0;
     virtual int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) = 0;
     virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
@@ -683,6 +684,59 @@ struct Solver final : SolverBase {
         *v = last_S;
         return 0;
     }
+    // ------------------------------------------------------------ checkpoint / restart
+    struct CkptHeader {
+        char magic[8];
+        int32_t version, case_rule, nx, ny, nz, z_begin, z_end, precision, storage, reserved;
+        int64_t steps, qstride, elems;
+    };
+    int checkpoint(const char *path, bool save) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "checkpoint before initialize");
+        if (in_step) FAIL(LBM_ERR_STATE, "checkpoint inside lbm_step_begin / lbm_step_end");
+        if (!path) FAIL(LBM_ERR_ARG, "null path");
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(st));
+        // the buffer the next step pulls from holds the whole state (the other one is overwritten),
+        // except for the never-rewritten static slots, which initialize() put into both
+        const size_t elems = (size_t)qstride * Q;
+        CkptHeader hd{};
+        memcpy(hd.magic, "LBMB200", 8);
+        hd.version = 1, hd.case_rule = d.case_rule, hd.nx = d.nx, hd.ny = d.ny, hd.nz = d.nz;
+        hd.z_begin = d.z_begin, hd.z_end = d.z_end, hd.precision = d.precision, hd.storage = d.storage;
+        hd.steps = steps, hd.qstride = qstride, hd.elems = (int64_t)elems;
+        std::vector<T> host(elems);
+        if (save) {
+            FILE *f = fopen(path, "wb");
+            if (!f) FAIL(LBM_ERR_IO, "cannot write '%s'", path);
+            CK(cudaMemcpy(host.data(), d_cur, elems * sizeof(T), cudaMemcpyDeviceToHost));
+            bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(host.data(), sizeof(T), elems, f) == elems;
+            fclose(f);
+            if (!ok) FAIL(LBM_ERR_IO, "short write to '%s'", path);
+            return 0;
+        }
+        FILE *f = fopen(path, "rb");
+        if (!f) FAIL(LBM_ERR_IO, "cannot open '%s'", path);
+        CkptHeader in{};
+        bool ok = fread(&in, sizeof in, 1, f) == 1;
+        if (ok && (memcmp(in.magic, hd.magic, 8) || in.version != 1 || in.case_rule != hd.case_rule || in.nx != hd.nx ||
+                   in.ny != hd.ny || in.nz != hd.nz || in.z_begin != hd.z_begin || in.z_end != hd.z_end ||
+                   in.precision != hd.precision || in.storage != hd.storage || in.qstride != hd.qstride ||
+                   in.elems != hd.elems)) {
+            fclose(f);
+            FAIL(LBM_ERR_ARG, "checkpoint '%s' was written for a different case / slab / precision / storage", path);
+        }
+        ok = ok && fread(host.data(), sizeof(T), elems, f) == elems;
+        fclose(f);
+        if (!ok) FAIL(LBM_ERR_IO, "short read from '%s'", path);
+        steps = in.steps;
+        // two-buffer storage alternates with the step parity; keep "current" consistent with it
+        d_cur = (d_fb != d_fa && (steps & 1)) ? d_fb : d_fa;
+        d_nxt = d_cur == d_fa ? d_fb : d_fa;
+        CK(cudaMemcpy(d_cur, host.data(), elems * sizeof(T), cudaMemcpyHostToDevice));
+        have_moments = false;
+        return 0;
+    }
+
     int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "p2p_export before initialize");
         if (d.storage == LBM_STORE_DENSE_AA) FAIL(LBM_ERR_ARG, "in-place storage has no slab support");
@@ -1231,6 +1285,8 @@ int lbm_p2p_attach(lbm_handle h, int32_t side, void *pa, void *pb, int64_t pqs, 
     H_OR_FAIL;
     return h->s->p2p_attach(side, pa, pb, pqs, pc0);
 }
+int lbm_checkpoint_save(lbm_handle h, const char *path) { H_OR_FAIL; return h->s->checkpoint(path, true); }
+int lbm_checkpoint_load(lbm_handle h, const char *path) { H_OR_FAIL; return h->s->checkpoint(path, false); }
 int lbm_step_begin(lbm_handle h, int32_t flags) { H_OR_FAIL; return h->s->step_begin(flags); }
 int lbm_step_interior(lbm_handle h) { H_OR_FAIL; return h->s->step_interior(); }
 int lbm_step_end(lbm_handle h) { H_OR_FAIL; return h->s->step_end(); }
