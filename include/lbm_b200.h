@@ -253,7 +253,9 @@ int lbm_last_velsum(lbm_handle h, double *value);
  * another GPU mapped over NVLink, or of another handle on the same GPU).  Only fluid threads exist,
  * so solid halo slots are never clobbered and no unpack mask is needed.  The caller still has to
  * order the steps: a slab may start step t+1 only after both neighbours finished step t.
- *   lbm_p2p_export: IPC handles + raw pointers of the two population buffers, their q stride, and the
+ *   lbm_p2p_export: IPC handles + raw pointers of the two population buffers, the byte offset of each
+ *                   buffer inside the allocation its handle maps (small cudaMalloc blocks are
+ *                   sub-allocated: two buffers can share one handle), their q stride, and the
  *                   cell/compact offset of this slab's low and high halo planes;
  *   lbm_p2p_open / lbm_p2p_close: map / unmap another process's buffer (cudaIpcOpenMemHandle);
  *   lbm_p2p_attach: side 0/1 now pushes into the neighbour's buffers (peer_a/peer_b in the same order
@@ -261,7 +263,8 @@ int lbm_last_velsum(lbm_handle h, double *value);
 typedef struct {
     unsigned char bytes[64];
 } lbm_ipc_handle;
-int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t *qstride, int64_t halo_c0[2]);
+int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t byte_offset[2], int64_t *qstride,
+                   int64_t halo_c0[2]);
 int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr);
 int lbm_p2p_close(void *dev_ptr);
 int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64_t peer_qstride, int64_t peer_halo_c0);

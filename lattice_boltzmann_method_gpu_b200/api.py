@@ -128,7 +128,7 @@ def load_library() -> C.CDLL:
         "lbm_step_interior": ([vp], C.c_int),
         "lbm_step_end": ([vp], C.c_int),
         "lbm_last_velsum": ([vp, P(dbl)], C.c_int),
-        "lbm_p2p_export": ([vp, vp, P(vp), P(i64), P(i64)], C.c_int),
+        "lbm_p2p_export": ([vp, vp, P(vp), P(i64), P(i64), P(i64)], C.c_int),
         "lbm_p2p_open": ([vp, P(vp)], C.c_int),
         "lbm_p2p_close": ([vp], C.c_int),
         "lbm_p2p_attach": ([vp, i32, vp, vp, i64, i64], C.c_int),
@@ -276,14 +276,16 @@ class Case:
 
     # -- fused peer-to-peer halo exchange
     def p2p_export(self):
-        """(two 64-byte IPC handles, two raw device pointers, q stride, [low, high] halo-plane offsets)"""
+        """(two 64-byte IPC handles, two raw device pointers, q stride, [low, high] halo-plane offsets,
+        byte offsets of the two buffers inside the allocations their handles map)"""
         handles = (C.c_ubyte * 128)()
         ptrs = (C.c_void_p * 2)()
+        boff = (C.c_int64 * 2)()
         qs = C.c_int64()
         c0 = (C.c_int64 * 2)()
-        self._ck(self._L.lbm_p2p_export(self._h, handles, ptrs, C.byref(qs), c0))
+        self._ck(self._L.lbm_p2p_export(self._h, handles, ptrs, boff, C.byref(qs), c0))
         raw = bytes(handles)
-        return [raw[:64], raw[64:]], [ptrs[0], ptrs[1]], qs.value, [c0[0], c0[1]]
+        return [raw[:64], raw[64:]], [ptrs[0], ptrs[1]], qs.value, [c0[0], c0[1]], [boff[0], boff[1]]
 
     def p2p_attach(self, side: int, peer_a: int, peer_b: int, peer_qstride: int, peer_halo_c0: int):
         self._ck(self._L.lbm_p2p_attach(self._h, side, peer_a, peer_b, peer_qstride, peer_halo_c0))
@@ -364,14 +366,21 @@ class Case:
         return self._L.lbm_stream(self._h)
 
 
+_opened_ipc = {}
+
+
 def p2p_open(handle_bytes: bytes) -> int:
-    """map a population buffer exported by another process (cudaIpcOpenMemHandle)"""
+    """map an allocation exported by another process (cudaIpcOpenMemHandle); an allocation can be
+    opened only once per process, so mappings are cached by handle"""
+    if handle_bytes in _opened_ipc:
+        return _opened_ipc[handle_bytes]
     L = load_library()
     buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
     ptr = C.c_void_p()
     rc = L.lbm_p2p_open(buf, C.byref(ptr))
     if rc:
         raise LbmError(rc, L.lbm_last_error(None).decode())
+    _opened_ipc[handle_bytes] = ptr.value
     return ptr.value
 
 

@@ -61,7 +61,7 @@ struct SolverBase {
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
     virtual int checkpoint(const char *path, bool save) = 0;
-    virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) = 0;
+    virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0) = 0;
     virtual int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) = 0;
     virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
     virtual int sync() = 0;
@@ -737,7 +737,7 @@ struct Solver final : SolverBase {
         return 0;
     }
 
-    int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *qs, int64_t *halo_c0) override {
+    int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "p2p_export before initialize");
         if (d.storage == LBM_STORE_DENSE_AA) FAIL(LBM_ERR_ARG, "in-place storage has no slab support");
         CK(cudaSetDevice(d.device));
@@ -751,6 +751,19 @@ struct Solver final : SolverBase {
                 memcpy(&h2[k], &ih, sizeof ih);
             }
             if (ptrs) ptrs[k] = bufs[k];
+            if (boff) {
+                // offset of the buffer inside the allocation the IPC handle stands for (driver entry point
+                // fetched at run time: no link-time dependency on libcuda)
+                typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+                void *fn = nullptr;
+                cudaDriverEntryPointQueryResult qr;
+                CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+                unsigned long long base = 0;
+                size_t sz = 0;
+                if (!fn || ((range_fn)fn)(&base, &sz, (unsigned long long)(uintptr_t)bufs[k]) != 0)
+                    FAIL(LBM_ERR_CUDA, "cuMemGetAddressRange failed");
+                boff[k] = (int64_t)((unsigned long long)(uintptr_t)bufs[k] - base);
+            }
         }
         if (qs) *qs = qstride;
         if (halo_c0) {
@@ -1265,9 +1278,10 @@ int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_
     H_OR_FAIL;
     return h->s->halo_buffers(side, send, recv, send_bytes, recv_bytes);
 }
-int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t *qstride, int64_t halo_c0[2]) {
+int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t byte_offset[2], int64_t *qstride,
+                   int64_t halo_c0[2]) {
     H_OR_FAIL;
-    return h->s->p2p_export(handles, ptrs, qstride, halo_c0);
+    return h->s->p2p_export(handles, ptrs, byte_offset, qstride, halo_c0);
 }
 int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr) {
     if (!handle || !dev_ptr) return LBM_ERR_ARG;

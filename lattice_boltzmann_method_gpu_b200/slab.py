@@ -114,13 +114,13 @@ class SlabCase(api.Case):
         import torch
         import torch.distributed as dist
 
-        handles, _, qs, c0 = self.p2p_export()
-        mine = {"handles": handles, "qs": qs, "c0": c0}
+        handles, _, qs, c0, boff = self.p2p_export()
+        mine = {"handles": handles, "qs": qs, "c0": c0, "boff": boff}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
         for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
             if 0 <= nb < self.world:
-                pa, pb = (api.p2p_open(h) for h in everyone[nb]["handles"])
+                pa, pb = (api.p2p_open(h) + o for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]))
                 # my low face feeds the neighbour's HIGH halo plane and vice versa
                 self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["c0"][1 - side])
         self._tick = torch.zeros(1, device="cuda")

@@ -162,7 +162,7 @@ def test_fused_peer_store_halo_exchange(name, n, P, storage_name):
     for r, c in enumerate(cs):
         for side, nb in ((0, r - 1), (1, r + 1)):
             if 0 <= nb < P:
-                _, ptrs, qs, c0 = exp[nb]
+                _, ptrs, qs, c0, _ = exp[nb]
                 c.p2p_attach(side, ptrs[0], ptrs[1], qs, c0[1 - side])
     launches0 = sum(c.launch_count for c in cs)
     for it in range(steps):
