@@ -235,8 +235,8 @@ def run_ours(args):
     def setup(c):
         if world > 1:
             c.setup()
-            if args.halo == "p2p":
-                c.enable_p2p()
+            if args.halo == "p2p" and not c.enable_p2p():
+                args.halo = "nccl (peer mapping unavailable)"
         else:
             c.geo_pre()
             c.index_transform()

@@ -175,7 +175,8 @@ struct Solver final : SolverBase {
         box.z0 = own_z0 - (lo_halo ? 1 : 0), box.z1 = own_z1 + (hi_halo ? 1 : 0);
         ext = box;
         ext.z0 = std::max(0, own_z0 - 3), ext.z1 = std::min(d.nz, own_z1 + 3);
-        if (box.cells() * 19 >= (1LL << 40)) FAIL(LBM_ERR_ARG, "box too large");
+        // compact indices are int32, like the reference's h_index (bifurcation.cu:22)
+        if (box.cells() >= (1LL << 31)) FAIL(LBM_ERR_ARG, "slab of %lld cells exceeds the int32 index range: use more z-slabs", box.cells());
         rules.case_rule = d.case_rule;
         rules.n_open = d.n_openings;
         for (int i = 0; i < d.n_openings; i++) rules.open[i] = d.openings[i];

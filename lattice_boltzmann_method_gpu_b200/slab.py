@@ -118,14 +118,27 @@ class SlabCase(api.Case):
         mine = {"handles": handles, "qs": qs, "c0": c0, "boff": boff}
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
-        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
-            if 0 <= nb < self.world:
-                pa, pb = (api.p2p_open(h) + o for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]))
-                # my low face feeds the neighbour's HIGH halo plane and vice versa
-                self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["c0"][1 - side])
+        ok, attached = 1, []
+        try:
+            for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+                if 0 <= nb < self.world:
+                    pa, pb = (api.p2p_open(h) + o for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]))
+                    # my low face feeds the neighbour's HIGH halo plane and vice versa
+                    self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["c0"][1 - side])
+                    attached.append(side)
+        except api.LbmError:
+            ok = 0
+        # all ranks or none: a rank that cannot map its neighbour (no peer access / IPC) sends everyone
+        # back to the pack + NCCL path
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            for side in attached:
+                self.p2p_attach(side, None, None, 0, 0)
+            return False
         self._tick = torch.zeros(1, device="cuda")
         self._p2p = True
-        dist.barrier(group=self.group)
+        return True
 
     def _wrap_buffers(self):
         import torch
