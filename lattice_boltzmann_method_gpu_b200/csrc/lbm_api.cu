@@ -120,6 +120,9 @@ struct Solver final : SolverBase {
     bool offset_set = false;
     size_t scratch_ints = 0;
     double last_S = 0.0;
+    std::vector<long long> plane_first;  // [planes of the state box + 1] global compact id each plane starts at
+    T *d_stage = nullptr;                // staging of get_fields (dense storage), one plane group at a time
+    size_t stage_elems = 0;
     long long pend_i0 = 0, pend_i1 = 0;
     bool interior_pending = false;
     // fused peer-to-peer halo exchange (per side: neighbour's two buffers, q stride, halo offset)
@@ -146,7 +149,7 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
-        fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
+        fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -318,8 +321,16 @@ struct Solver final : SolverBase {
         }
         scratch_ints = compact_scratch_ints(box.cells());
         if (!d_scratch && dalloc(&d_scratch, scratch_ints)) return LBM_ERR_NOMEM;
-        CK(launch_compact(d_label, d_index, box.cells(), box.px, box.nx, store_all(), (long long)compact_first - n_lo,
-                          d_scratch, scratch_ints, d_cnt + 2, st));
+        const int nzl = box.z1 - box.z0;
+        long long *d_pf = nullptr;
+        CK(cudaMalloc((void **)&d_pf, (size_t)nzl * sizeof(long long)));
+        cudaError_t ce = launch_compact(d_label, d_index, box.cells(), box.px, box.nx, store_all(),
+                                        (long long)compact_first - n_lo, d_scratch, scratch_ints, d_cnt + 2, box.plane, d_pf, st);
+        plane_first.assign((size_t)nzl + 1, 0);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(plane_first.data(), d_pf, (size_t)nzl * sizeof(long long), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        cudaFree(d_pf);
+        CK(ce);
         launches += 3;
         // node words, segment classes, int8 labels
         if (!d_node) {
@@ -335,6 +346,7 @@ struct Solver final : SolverBase {
         CK(cudaStreamSynchronize(st));
         nfluid = nf;
         n_lo_stored = n_lo, stored_box = nbox, sp_first = (long long)compact_first - n_lo;
+        plane_first[(size_t)(box.z1 - box.z0)] = sp_first + nbox;
         have_index = true;
         if (nlat) *nlat = compact_total;
         return 0;
@@ -840,19 +852,34 @@ struct Solver final : SolverBase {
             if (count) *count = stored_own;
             return 0;
         }
-        T *tmp = nullptr;
-        CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * 4 * sizeof(T)));
-        cudaError_t e = cudaMemsetAsync(tmp, 0, n * 4 * sizeof(T), st);
-        if (e == cudaSuccess)
-            e = launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, own_z0, own_z1, fluid_label,
-                                        compact_first, tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, st);
-        launches++;
-        void *outs[4] = {rho, ux, uy, uz};
-        for (int k = 0; k < 4 && e == cudaSuccess; k++)
-            if (outs[k]) e = cudaMemcpyAsync(outs[k], tmp + k * n, n * sizeof(T), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFree(tmp);
-        CK(e);
+        // dense storage: gather into compact order one group of planes at a time through a small
+        // persistent staging buffer (the kernel is ~1 % of the D2H copy time)
+        const long long group_cells = 32LL << 20;
+        const int gplanes = (int)std::max<long long>(1, group_cells / box.plane);
+        long long maxn = 1;
+        for (int z = own_z0; z < own_z1; z += gplanes) {
+            const int zb = std::min(own_z1, z + gplanes);
+            maxn = std::max(maxn, plane_first[(size_t)(zb - box.z0)] - plane_first[(size_t)(z - box.z0)]);
+        }
+        if ((size_t)maxn * 4 > stage_elems) {
+            if (d_stage) cudaFree(d_stage), d_stage = nullptr;
+            stage_elems = (size_t)maxn * 4;
+            CK(cudaMalloc((void **)&d_stage, stage_elems * sizeof(T)));
+        }
+        char *outs[4] = {(char *)rho, (char *)ux, (char *)uy, (char *)uz};
+        for (int z = own_z0; z < own_z1; z += gplanes) {
+            const int zb = std::min(own_z1, z + gplanes);
+            const long long f0 = plane_first[(size_t)(z - box.z0)], cnt = plane_first[(size_t)(zb - box.z0)] - f0;
+            if (cnt <= 0) continue;
+            CK(launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, z, zb, fluid_label, f0, d_stage,
+                                       d_stage + maxn, d_stage + 2 * maxn, d_stage + 3 * maxn, st));
+            launches++;
+            for (int k = 0; k < 4; k++)
+                if (outs[k])
+                    CK(cudaMemcpyAsync(outs[k] + (size_t)(f0 - compact_first) * sizeof(T), d_stage + (size_t)k * maxn,
+                                       (size_t)cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
         if (first) *first = compact_first;
         if (count) *count = stored_own;
         return 0;

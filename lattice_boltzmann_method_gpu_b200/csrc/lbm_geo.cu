@@ -235,7 +235,8 @@ __global__ void k_scan_tiles(const int32_t *tile_count, long long *tile_offset, 
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 __global__ void k_scatter_index(const int32_t *label, int32_t *index, long long cells, StoredRule sr,
-                                long long base_index, const long long *tile_offset) {
+                                long long base_index, const long long *tile_offset, long long plane,
+                                long long *plane_first) {
     long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
     int flags[SCAN_ITEMS];
     int cnt = 0;
@@ -252,6 +253,7 @@ __global__ void k_scatter_index(const int32_t *label, int32_t *index, long long 
     for (int i = 0; i < SCAN_ITEMS; i++) {
         long long c = base + i;
         if (c < cells) {
+            if (plane_first && c % plane == 0) plane_first[c / plane] = run;  // compact id the plane starts at
             index[c] = flags[i] ? (int32_t)run : -1;
             run += flags[i];
         }
@@ -627,7 +629,7 @@ size_t compact_scratch_ints(long long cells) {
 }
 cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells, int px, int nx, int all,
                            long long base, int32_t *scratch, size_t scratch_ints, long long *total_out_dev,
-                           cudaStream_t s) {
+                           long long plane, long long *plane_first_dev, cudaStream_t s) {
     StoredRule sr{px, nx, all};
     long long ntiles = (cells + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)(3 * ntiles + 4) > scratch_ints) return cudaErrorInvalidValue;
@@ -636,7 +638,7 @@ cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells
     long long *offsets = reinterpret_cast<long long *>(scratch + ((ntiles + 1) & ~1LL));
     k_tile_counts<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, cells, sr, counts);
     k_scan_tiles<<<1, SCAN_BLOCK, 0, s>>>(counts, offsets, (int)ntiles, total_out_dev);
-    k_scatter_index<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, index, cells, sr, base, offsets);
+    k_scatter_index<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, index, cells, sr, base, offsets, plane, plane_first_dev);
     return cudaGetLastError();
 }
 cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,

@@ -100,9 +100,10 @@ cudaError_t launch_make_flag_pos(uint8_t *flag, Box ext, cudaStream_t s);
 cudaError_t launch_labels(const uint8_t *flag, int32_t *label, Box ext, GeoRules r, cudaStream_t s);
 cudaError_t launch_mark(int32_t *label, Box ext, GeoRules r, cudaStream_t s);
 // exclusive scan of (label != 0) over `cells` cells; index = running count + base, or -1
+// plane_first_dev (optional, [cells/plane]): compact id each z-plane starts at
 cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells, int px, int nx, int all,
                            long long base, int32_t *scratch, size_t scratch_ints, long long *total_out_dev,
-                           cudaStream_t s);
+                           long long plane, long long *plane_first_dev, cudaStream_t s);
 size_t compact_scratch_ints(long long cells);
 cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
                                 cudaStream_t s);
