@@ -5,6 +5,7 @@
 // There is deliberately no CPU fallback: without a CUDA device lbm_create
 // fails with LBM_ERR_NO_DEVICE.
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -949,39 +950,47 @@ struct Solver final : SolverBase {
         else ofs << "ORIGIN " << std::round(NX / 2) * CH << ' ' << std::round(NY / 2) * CH << ' ' << .0 << endl;
         ofs << "POINT_DATA  " << (x1 - x0) * (y1 - y0) * (z1 - z0) << endl;
         auto idx_of = [&](int x, int y, int z) { return w_index[(size_t)x + (size_t)NX * ((size_t)y + (size_t)NY * z)]; };
+        // The bodies: the same characters `ofs << value << ' '` produces (default ostream float format =
+        // %g with 6 significant digits = std::to_chars general/6), formatted into one buffer -- at 512^3
+        // the reference's ASCII writer would otherwise dominate the run.
+        std::string buf;
+        buf.reserve((size_t)(x1 - x0) * (y1 - y0) * (z1 - z0) * 3 * 12 + 64);
+        char tmp[48];
+        auto put = [&](auto v) {
+            auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::general, 6);
+            buf.append(tmp, r.ptr);
+            buf.push_back(' ');
+        };
         if (d.case_rule == LBM_CASE_GEO_OPENINGS) {
-            ofs << "SCALARS DENSITY float" << endl << "LOOKUP_TABLE default" << endl;
+            buf += "SCALARS DENSITY float\nLOOKUP_TABLE default\n";
             for (int z = z0; z < z1; z++)
                 for (int y = y0; y < y1; y++)
                     for (int x = x0; x < x1; x++) {
                         int i = idx_of(x, y, z);
-                        if (i >= 0) ofs << (float)w_rho[i] * C_rho << ' ';
-                        else ofs << 0.0f << ' ';
+                        put(i >= 0 ? (float)w_rho[i] * C_rho : 0.0f);
                     }
-            ofs << endl;
-            ofs << "SCALARS PRESSURE float" << endl << "LOOKUP_TABLE default" << endl;
+            buf += "\nSCALARS PRESSURE float\nLOOKUP_TABLE default\n";
             for (int z = z0; z < z1; z++)
                 for (int y = y0; y < y1; y++)
                     for (int x = x0; x < x1; x++) {
                         int i = idx_of(x, y, z);
-                        if (i >= 0) ofs << (float)w_rho[i] * C_pre / 3.0 << ' ';
-                        else ofs << 0.0f << ' ';
+                        if (i >= 0) put((float)w_rho[i] * C_pre / 3.0);  // double, as in cor.cu:983
+                        else put(0.0f);
                     }
-            ofs << endl;
+            buf += "\n";
         }
-        ofs << "VECTORS VELOCITY float" << endl;
+        buf += "VECTORS VELOCITY float\n";
         for (int z = z0; z < z1; z++)
             for (int y = y0; y < y1; y++)
                 for (int x = x0; x < x1; x++) {
                     int i = idx_of(x, y, z);
                     if (i >= 0) {
-                        ofs << (float)w_ux[i] * C_U << ' ';
-                        ofs << (float)w_uy[i] * C_U << ' ';
-                        ofs << (float)w_uz[i] * C_U << ' ';
+                        put((float)w_ux[i] * C_U), put((float)w_uy[i] * C_U), put((float)w_uz[i] * C_U);
                     } else {
-                        ofs << 0 << ' ' << 0 << ' ' << 0 << ' ';
+                        buf += "0 0 0 ";
                     }
                 }
+        ofs.write(buf.data(), (std::streamsize)buf.size());
         ofs.close();
         return 0;
     }
