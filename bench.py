@@ -6,7 +6,9 @@
 
 Workload (BASELINE.json configs[2]): dense lid-driven cavity 512^3, fp64, one B200.
 At N > 1 (torchrun, one rank per GPU) the domain is 512 x 512 x (512*N), z-slab sharded, one
-512^3 slab per GPU (weak scaling), halo exchange of the 5 crossing populations per face over NCCL.
+512^3 slab per GPU (weak scaling); the step kernel stores the 5 crossing populations per face cell
+straight into the neighbour GPU's buffer (CUDA IPC peer memory over NVLink); --halo nccl packs and
+sends them with NCCL instead (two-buffer storage only).
 
 A "step" is one pass of the hot path: one fused pull-stream + collide (+ link-wise boundaries)
 launch over every fluid node.  `value` = fluid-node updates / s / 1e6 with all state resident in HBM,
@@ -233,17 +235,26 @@ def run_ours(args):
         return slab.SlabCase(d) if world > 1 else L.Case(d)
 
     def setup(c):
-        if world > 1:
-            c.setup()
-            if args.halo == "p2p" and not c.enable_p2p():
-                args.halo = "nccl (peer mapping unavailable)"
-        else:
+        """returns the case ready to step (a different one if the peer mapping is unavailable)"""
+        nonlocal storage
+        if world == 1:
             c.geo_pre()
             c.index_transform()
             c.initialize()
+            return c
+        if args.halo != "p2p" and storage == L.STORE_DENSE_AA:
+            raise SystemExit("--storage aa exchanges slab faces by peer stores only: use --halo p2p or --storage ab")
+        c.setup()
+        if args.halo == "p2p" and not c.enable_p2p():  # the decision is all-reduced: every rank takes the same branch
+            args.halo = "nccl (peer mapping unavailable)"
+            if storage == L.STORE_DENSE_AA:
+                c.close()
+                storage, args.storage = L.STORE_DENSE_AB, "ab"
+                c = build_case()
+                c.setup()
+        return c
 
-    c = build_case()
-    setup(c)
+    c = setup(build_case())
     nfluid_local = c.num_fluid
     nfluid = nfluid_local
     if world > 1:
@@ -297,8 +308,7 @@ def run_ours(args):
         outs = [p.numpy() for p in pinned]
         barrier()
         t0 = time.perf_counter()
-        c = build_case()
-        setup(c)
+        c = setup(build_case())
         t1 = time.perf_counter()
         c.step(args.steps)
         t2 = time.perf_counter()
@@ -359,7 +369,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--storage", default="ab", choices=["ab", "aa"])
+    ap.add_argument("--storage", default="aa", choices=["ab", "aa"],
+                    help="aa: one population buffer streamed in place (default); ab: two buffers")
     ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
                     help="global box (default n x n x n*gpus, i.e. weak scaling with one n^3 slab per GPU)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],

@@ -259,15 +259,19 @@ int lbm_last_velsum(lbm_handle h, double *value);
  *                   cell/compact offset of this slab's low and high halo planes;
  *   lbm_p2p_open / lbm_p2p_close: map / unmap another process's buffer (cudaIpcOpenMemHandle);
  *   lbm_p2p_attach: side 0/1 now pushes into the neighbour's buffers (peer_a/peer_b in the same order
- *                   as exported) at peer_halo_c0 = the neighbour's halo-plane offset facing this slab. */
+ *                   as exported) at peer_halo_c0 = the neighbour's halo-plane offset facing this slab;
+ *                   peer_face_c0 = offset of the neighbour's outermost OWNED plane on that side, which
+ *                   the odd step of the in-place (AA) storage pushes into.  With in-place storage the
+ *                   peer stores are the only transport: attach before stepping a slab. */
 typedef struct {
     unsigned char bytes[64];
 } lbm_ipc_handle;
 int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t byte_offset[2], int64_t *qstride,
-                   int64_t halo_c0[2]);
+                   int64_t halo_c0[2], int64_t face_c0[2]);
 int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr);
 int lbm_p2p_close(void *dev_ptr);
-int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64_t peer_qstride, int64_t peer_halo_c0);
+int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64_t peer_qstride, int64_t peer_halo_c0,
+                   int64_t peer_face_c0);
 
 /* cudaStream_t of the handle as an opaque pointer (for event / NCCL interop) */
 void *lbm_stream(lbm_handle h);

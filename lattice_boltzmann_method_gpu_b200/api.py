@@ -128,10 +128,10 @@ def load_library() -> C.CDLL:
         "lbm_step_interior": ([vp], C.c_int),
         "lbm_step_end": ([vp], C.c_int),
         "lbm_last_velsum": ([vp, P(dbl)], C.c_int),
-        "lbm_p2p_export": ([vp, vp, P(vp), P(i64), P(i64), P(i64)], C.c_int),
+        "lbm_p2p_export": ([vp, vp, P(vp), P(i64), P(i64), P(i64), P(i64)], C.c_int),
         "lbm_p2p_open": ([vp, P(vp)], C.c_int),
         "lbm_p2p_close": ([vp], C.c_int),
-        "lbm_p2p_attach": ([vp, i32, vp, vp, i64, i64], C.c_int),
+        "lbm_p2p_attach": ([vp, i32, vp, vp, i64, i64, i64], C.c_int),
         "lbm_checkpoint_save": ([vp, C.c_char_p], C.c_int),
         "lbm_checkpoint_load": ([vp, C.c_char_p], C.c_int),
         "lbm_stream": ([vp], vp),
@@ -276,19 +276,21 @@ class Case:
 
     # -- fused peer-to-peer halo exchange
     def p2p_export(self):
-        """(two 64-byte IPC handles, two raw device pointers, q stride, [low, high] halo-plane offsets,
-        byte offsets of the two buffers inside the allocations their handles map)"""
+        """dict: two 64-byte IPC handles, two raw device pointers, q stride, [low, high] halo-plane offsets,
+        [low, high] outermost-owned-plane offsets, byte offsets of the buffers inside their allocations"""
         handles = (C.c_ubyte * 128)()
         ptrs = (C.c_void_p * 2)()
         boff = (C.c_int64 * 2)()
         qs = C.c_int64()
         c0 = (C.c_int64 * 2)()
-        self._ck(self._L.lbm_p2p_export(self._h, handles, ptrs, boff, C.byref(qs), c0))
+        f0 = (C.c_int64 * 2)()
+        self._ck(self._L.lbm_p2p_export(self._h, handles, ptrs, boff, C.byref(qs), c0, f0))
         raw = bytes(handles)
-        return [raw[:64], raw[64:]], [ptrs[0], ptrs[1]], qs.value, [c0[0], c0[1]], [boff[0], boff[1]]
+        return {"handles": [raw[:64], raw[64:]], "ptrs": [ptrs[0], ptrs[1]], "qs": qs.value, "halo_c0": [c0[0], c0[1]],
+                "face_c0": [f0[0], f0[1]], "boff": [boff[0], boff[1]]}
 
-    def p2p_attach(self, side: int, peer_a: int, peer_b: int, peer_qstride: int, peer_halo_c0: int):
-        self._ck(self._L.lbm_p2p_attach(self._h, side, peer_a, peer_b, peer_qstride, peer_halo_c0))
+    def p2p_attach(self, side: int, peer_a, peer_b, peer_qstride: int = 0, peer_halo_c0: int = 0, peer_face_c0: int = 0):
+        self._ck(self._L.lbm_p2p_attach(self._h, side, peer_a, peer_b, peer_qstride, peer_halo_c0, peer_face_c0))
 
     def residual(self, kind: int = RES_VELSUM) -> float:
         v = C.c_double()

@@ -62,8 +62,8 @@ struct SolverBase {
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
     virtual int checkpoint(const char *path, bool save) = 0;
-    virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0) = 0;
-    virtual int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) = 0;
+    virtual int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0, int64_t *face_c0) = 0;
+    virtual int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0, int64_t pown) = 0;
     virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
     virtual int sync() = 0;
     virtual void *stream_ptr() = 0;
@@ -128,7 +128,7 @@ struct Solver final : SolverBase {
     bool interior_pending = false;
     // fused peer-to-peer halo exchange (per side: neighbour's two buffers, q stride, halo offset)
     T *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    long long peer_qs[2] = {0, 0}, peer_c0[2] = {0, 0};
+    long long peer_qs[2] = {0, 0}, peer_c0[2] = {0, 0}, peer_own[2] = {0, 0};
     // sparse storage (reference compact order + run segments)
     bool sparse = false;
     long long n_lo_stored = 0, stored_box = 0;   // stored nodes of the low halo plane / of the whole state box
@@ -419,7 +419,6 @@ struct Solver final : SolverBase {
         if (d.storage != LBM_STORE_DENSE_AB && d.storage != LBM_STORE_DENSE_AA)
             FAIL(LBM_ERR_ARG, "unknown storage %d", d.storage);
         const bool aa = d.storage == LBM_STORE_DENSE_AA;
-        if (aa && (lo_halo || hi_halo)) FAIL(LBM_ERR_ARG, "in-place (AA) storage is single-domain only in this build");
         if (d.case_rule == LBM_CASE_GEO_Y_INOUT && !have_planes) {
             h_in.assign((size_t)d.nx * d.nz, 0.f), h_out = h_in;
             int r = upload_planes();
@@ -575,11 +574,11 @@ struct Solver final : SolverBase {
         // face_sides bit 0: this range is the lowest owned plane, bit 1: the highest -> push to attached peers
         const int which = d_nxt == d_fa ? 0 : 1;
         if ((face_sides & 2) && peer_buf[1][which]) {
-            p.peer_up = peer_buf[1][which], p.peer_up_qs = peer_qs[1], p.peer_up_c0 = peer_c0[1];
+            p.peer_up = peer_buf[1][which], p.peer_up_qs = peer_qs[1], p.peer_up_c0 = peer_c0[1], p.peer_up_own = peer_own[1];
             p.face_c0 = sparse ? face_id0[1] : c0;
         }
         if ((face_sides & 1) && peer_buf[0][which]) {
-            p.peer_dn = peer_buf[0][which], p.peer_dn_qs = peer_qs[0], p.peer_dn_c0 = peer_c0[0];
+            p.peer_dn = peer_buf[0][which], p.peer_dn_qs = peer_qs[0], p.peer_dn_c0 = peer_c0[0], p.peer_dn_own = peer_own[0];
             p.face_c0 = sparse ? face_id0[0] : c0;
         }
         if (sparse) {
@@ -630,6 +629,8 @@ struct Solver final : SolverBase {
         if (in_step) FAIL(LBM_ERR_STATE, "lbm_step_begin called twice");
         CK(cudaSetDevice(d.device));
         const bool mom = flags & LBM_STEP_MOMENTS, res = flags & LBM_STEP_VELSUM;
+        if (d.storage == LBM_STORE_DENSE_AA && ((lo_halo && !peer_buf[0][0]) || (hi_halo && !peer_buf[1][0])))
+            FAIL(LBM_ERR_STATE, "in-place storage exchanges slab faces by peer stores only: call lbm_p2p_attach first");
         step_flags = flags;
         if (res) CK(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
         int r;
@@ -751,9 +752,8 @@ struct Solver final : SolverBase {
         return 0;
     }
 
-    int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0) override {
+    int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0, int64_t *face_c0) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "p2p_export before initialize");
-        if (d.storage == LBM_STORE_DENSE_AA) FAIL(LBM_ERR_ARG, "in-place storage has no slab support");
         CK(cudaSetDevice(d.device));
         static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(lbm_ipc_handle), "handle size");
         T *bufs[2] = {d_fa, d_fb};
@@ -784,15 +784,19 @@ struct Solver final : SolverBase {
             halo_c0[0] = sparse ? halo_id0[0] : 0;
             halo_c0[1] = sparse ? halo_id0[1] : (long long)(box.z1 - box.z0 - 1) * box.plane;
         }
+        if (face_c0) {
+            face_c0[0] = sparse ? face_id0[0] : plane_c(own_z0);
+            face_c0[1] = sparse ? face_id0[1] : plane_c(own_z1 - 1);
+        }
         return 0;
     }
-    int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0) override {
+    int p2p_attach(int side, void *pa, void *pb, int64_t pqs, int64_t pc0, int64_t pown) override {
         if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
         if (!have_init) FAIL(LBM_ERR_STATE, "p2p_attach before initialize");
         if (!(side == 0 ? lo_halo : hi_halo)) FAIL(LBM_ERR_ARG, "no neighbour on side %d", side);
         if ((pa == nullptr) != (pb == nullptr)) FAIL(LBM_ERR_ARG, "both peer buffers or none");
         peer_buf[side][0] = (T *)pa, peer_buf[side][1] = (T *)pb;
-        peer_qs[side] = pqs, peer_c0[side] = pc0;
+        peer_qs[side] = pqs, peer_c0[side] = pc0, peer_own[side] = pown;
         return 0;
     }
     int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) override {
@@ -1061,8 +1065,8 @@ struct Solver final : SolverBase {
     // ldc.cu:653-685 / pos.cu:986-1019: residual every step, cumulative tol_count.
     // Steps run in batches that end on save iterations; S_k of each step lands in
     // its own device slot, so the host applies the reference's stopping rule
-    // exactly without a sync per step.  Once the tolerance was hit for the
-    // first time the batch size drops to 1, so the loop stops on the same k.
+    // exactly without a sync per step; batch sizes shrink as tol_count approaches
+    // stag_max so that the loop stops on exactly the same k.
     int run_converge(int max_it, double tol_d, int stag_max, int time_save, int write_files, int *its,
                      double *res) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "run before initialize");
@@ -1075,10 +1079,12 @@ struct Solver final : SolverBase {
         const float tol = (float)tol_d;
         float residual = 0.f, sum_current = 0.f;
         int k = 0, tol_count = 0;
-        const int max_batch = std::max(1, std::min({ACC_SLOTS - 2, stag_max / 2, 32}));
+        const int max_batch = std::max(1, std::min(ACC_SLOTS - 2, 48));
         std::vector<double> S(ACC_SLOTS);
         while (k <= max_it && tol_count <= stag_max) {
-            int nb = tol_count > 0 ? 1 : max_batch;
+            // the loop cannot end by the tolerance rule in fewer than stag_max + 1 - tol_count more steps
+            // (at most one hit per step), so a batch of that many never overshoots the stopping iteration
+            int nb = std::min(max_batch, std::max(1, stag_max + 1 - tol_count));
             nb = std::min(nb, max_it - k + 1);
             // the batch covers iterations k .. k+nb-1; a save iteration inside must be the last one
             for (int j = 0; j < nb; j++)
@@ -1316,9 +1322,9 @@ int lbm_halo_buffers(lbm_handle h, int32_t side, void **send, void **recv, size_
     return h->s->halo_buffers(side, send, recv, send_bytes, recv_bytes);
 }
 int lbm_p2p_export(lbm_handle h, lbm_ipc_handle handles[2], void *ptrs[2], int64_t byte_offset[2], int64_t *qstride,
-                   int64_t halo_c0[2]) {
+                   int64_t halo_c0[2], int64_t face_c0[2]) {
     H_OR_FAIL;
-    return h->s->p2p_export(handles, ptrs, byte_offset, qstride, halo_c0);
+    return h->s->p2p_export(handles, ptrs, byte_offset, qstride, halo_c0, face_c0);
 }
 int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr) {
     if (!handle || !dev_ptr) return LBM_ERR_ARG;
@@ -1332,9 +1338,9 @@ int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr) {
     return LBM_OK;
 }
 int lbm_p2p_close(void *dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? LBM_OK : LBM_ERR_CUDA; }
-int lbm_p2p_attach(lbm_handle h, int32_t side, void *pa, void *pb, int64_t pqs, int64_t pc0) {
+int lbm_p2p_attach(lbm_handle h, int32_t side, void *pa, void *pb, int64_t pqs, int64_t pc0, int64_t pown) {
     H_OR_FAIL;
-    return h->s->p2p_attach(side, pa, pb, pqs, pc0);
+    return h->s->p2p_attach(side, pa, pb, pqs, pc0, pown);
 }
 int lbm_checkpoint_save(lbm_handle h, const char *path) { H_OR_FAIL; return h->s->checkpoint(path, true); }
 int lbm_checkpoint_load(lbm_handle h, const char *path) { H_OR_FAIL; return h->s->checkpoint(path, false); }

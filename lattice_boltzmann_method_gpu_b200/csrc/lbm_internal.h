@@ -75,7 +75,13 @@ struct StepParams {
     T *peer_up, *peer_dn;           // neighbour's destination buffer (peer / same-device memory) or null
     long long peer_up_qs, peer_dn_qs;   // its q stride
     long long peer_up_c0, peer_dn_c0;   // offset of its halo plane (cells, or compact ids for sparse)
+    long long peer_up_own, peer_dn_own; // offset of its outermost owned plane (AA odd step pushes there)
     long long face_c0;              // offset of this launch's plane (cell of c_begin / first compact id)
+    // per-direction base pointers of the dense kernels, so that an access is base[q] + c (one 64-bit
+    // add) instead of five integer instructions: pull_base[q][c] is the population direction q pulls
+    // for cell c, store_base[q][c] the slot its post-collision value goes to (storage mode folded in)
+    const T *pull_base[Q];
+    T *store_base[Q];
     int case_rule;                  // lbm_case_rule (initial-state rule, for static links in the AA odd step)
     T u_init;                       // lbm_case_desc.u_max
 };

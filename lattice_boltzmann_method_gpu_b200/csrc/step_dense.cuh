@@ -181,13 +181,13 @@ __device__ __forceinline__ float ld_spec_rw(const float *p) {
 }
 
 template <int MODE>
-__device__ __forceinline__ long long pull_index(int q, long long c, long long qs, long long off) {
+__host__ __device__ __forceinline__ long long pull_index(int q, long long c, long long qs, long long off) {
     if (MODE == MODE_AB) return (long long)q * qs + c - off;
     if (MODE == MODE_AA_EVEN) return (long long)q * qs + c;
     return (long long)oppq(q) * qs + c - off;
 }
 template <int MODE>
-__device__ __forceinline__ long long store_index(int q, long long c, long long qs, long long off) {
+__host__ __device__ __forceinline__ long long store_index(int q, long long c, long long qs, long long off) {
     if (MODE == MODE_AB) return (long long)q * qs + c;
     if (MODE == MODE_AA_EVEN) return (long long)oppq(q) * qs + c;
     return (long long)q * qs + c + off;
@@ -203,17 +203,25 @@ __device__ __forceinline__ long long slot_index(int q, long long c, long long qs
 // populations are already in f[]
 // Fused halo exchange: the populations that leave through a z face go straight into the neighbour
 // slab's halo plane (same x,y; `i` = offset inside the plane).  c_z=+1: q in {5,11,13,15,16}.
-template <typename T>
-__device__ __forceinline__ void push_to_peers(const StepParams<T> &p, long long i, const T (&f)[Q]) {
-    if (p.peer_up) {
-        T *d = p.peer_up + p.peer_up_c0 + i;
-        d[5 * p.peer_up_qs] = f[5], d[11 * p.peer_up_qs] = f[11], d[13 * p.peer_up_qs] = f[13];
-        d[15 * p.peer_up_qs] = f[15], d[16 * p.peer_up_qs] = f[16];
-    }
-    if (p.peer_dn) {
-        T *d = p.peer_dn + p.peer_dn_c0 + i;
-        d[6 * p.peer_dn_qs] = f[6], d[12 * p.peer_dn_qs] = f[12], d[14 * p.peer_dn_qs] = f[14];
-        d[17 * p.peer_dn_qs] = f[17], d[18 * p.peer_dn_qs] = f[18];
+// In-place storage: the even step leaves g_q(x) in slot opp(q) of x, which the neighbour's odd step
+// pulls -> the copy goes into slot opp(q) of the neighbour's halo plane; the odd step pushes g_q(x)
+// into slot q of the TARGET cell x + c_q, which for a face plane is a cell of the neighbour's
+// outermost owned plane (shifted by the in-plane part of c_q), fluid targets only.
+template <typename T, int MODE>
+__device__ __forceinline__ void push_to_peers(const StepParams<T> &p, long long i, uint32_t node, const T (&f)[Q]) {
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        if (czq(q) == 0) continue;
+        T *peer = czq(q) > 0 ? p.peer_up : p.peer_dn;
+        if (!peer) continue;
+        const long long qs = czq(q) > 0 ? p.peer_up_qs : p.peer_dn_qs;
+        if (MODE == MODE_AB) {
+            peer[(long long)q * qs + (czq(q) > 0 ? p.peer_up_c0 : p.peer_dn_c0) + i] = f[q];
+        } else if (MODE == MODE_AA_EVEN) {
+            peer[(long long)oppq(q) * qs + (czq(q) > 0 ? p.peer_up_c0 : p.peer_dn_c0) + i] = f[q];
+        } else if (!(node & (1u << oppq(q)))) {
+            peer[(long long)q * qs + (czq(q) > 0 ? p.peer_up_own : p.peer_dn_own) + i + cxq(q) + (long long)p.box.px * cyq(q)] = f[q];
+        }
     }
 }
 
@@ -228,19 +236,20 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
     T *dst = p.dst;
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
         if (MODE == MODE_AA_ODD) {
-            // push only into fluid targets: x + c_q is the source of link opp(q)
-            if (q == 0 || !(node & (1u << oppq(q)))) dst[store_index<MODE>(q, c, p.qstride, off)] = f[q];
+            // push only into fluid targets: x + c_q is the source of link opp(q); a target beyond a
+            // slab face lives in the neighbour's memory (push_to_peers)
+            const bool remote = (czq(q) > 0 && p.peer_up) || (czq(q) < 0 && p.peer_dn);
+            if (q == 0 || (!(node & (1u << oppq(q))) && !remote)) p.store_base[q][c] = f[q];
         } else {
-            dst[store_index<MODE>(q, c, p.qstride, off)] = f[q];
+            p.store_base[q][c] = f[q];
         }
     }
     if (MOMENTS) {
         p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
     }
     if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
-    if (MODE == MODE_AB && (p.peer_up || p.peer_dn)) push_to_peers<T>(p, c - p.face_c0, f);
+    if (p.peer_up || p.peer_dn) push_to_peers<T, MODE>(p, c - p.face_c0, node, f);
     if (node & NODE_LINKS) {
         // wall links: half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
         const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (WALL_READY ? wallw : p.wall[c]);
@@ -281,11 +290,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
         // every thread pulls; the buffers carry guards so all addresses are mapped
         node = p.node[c];
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-            const T *a = p.src + pull_index<MODE>(q, c, p.qstride, off);
-            f[q] = MODE == MODE_AB ? ld_spec(a) : ld_spec_rw(a);
-        }
+        for (int q = 0; q < Q; q++) f[q] = MODE == MODE_AB ? ld_spec(p.pull_base[q] + c) : ld_spec_rw(p.pull_base[q] + c);
         if (kind == SEG_EMPTY) return;
     } else {
         if (kind == SEG_EMPTY) return;
@@ -296,11 +301,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
     if (!(node & NODE_SKIP)) {
         if (!SPEC) {
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                const T *a = p.src + pull_index<MODE>(q, c, p.qstride, off);
-                f[q] = MODE == MODE_AB ? ld_stream(a) : *a;
-            }
+            for (int q = 0; q < Q; q++) f[q] = MODE == MODE_AB ? ld_stream(p.pull_base[q] + c) : p.pull_base[q][c];
         }
         finish_cell<T, STRICT, MOMENTS, RESID, MODE, !SPEC>(p, c, node, wallw, f, velsum);
     }
@@ -331,9 +332,26 @@ cudaError_t launch_cfg(const StepParams<T> &p, int storage, cudaStream_t s) {
     return launch_mode<T, STRICT, MOMENTS, RESID, C, MODE_AB>(p, s);
 }
 
+// host: fold the storage mode into the per-direction base pointers
+template <typename T, int MODE>
+void set_bases(StepParams<T> &p) {
+    for (int q = 0; q < Q; q++) {
+        const long long off = (long long)cxq(q) + (long long)p.box.px * cyq(q) + p.box.plane * czq(q);
+        p.pull_base[q] = p.src + pull_index<MODE>(q, 0, p.qstride, off);
+        p.store_base[q] = p.dst + store_index<MODE>(q, 0, p.qstride, off);
+    }
+}
+
 template <typename T, bool STRICT>
-cudaError_t launch_step_dense_impl(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s) {
-    if (p.c_end <= p.c_begin) return cudaSuccess;
+cudaError_t launch_step_dense_impl(const StepParams<T> &p_in, bool moments, bool resid, int storage, cudaStream_t s) {
+    if (p_in.c_end <= p_in.c_begin) return cudaSuccess;
+    StepParams<T> p = p_in;
+    if (storage == LBM_STORE_DENSE_AA) {
+        if (p.parity == 0) set_bases<T, MODE_AA_EVEN>(p);
+        else set_bases<T, MODE_AA_ODD>(p);
+    } else {
+        set_bases<T, MODE_AB>(p);
+    }
     if (moments && resid) return launch_cfg<T, STRICT, true, true>(p, storage, s);
     if (moments) return launch_cfg<T, STRICT, true, false>(p, storage, s);
     if (resid) return launch_cfg<T, STRICT, false, true>(p, storage, s);

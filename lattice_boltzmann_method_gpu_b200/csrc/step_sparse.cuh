@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
             p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
         }
         if (RESID) velsum = (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
-        if (p.peer_up || p.peer_dn) push_to_peers<T>(p, i - p.face_c0, f);  // compact ids: a plane is one id range
+        if (p.peer_up || p.peer_dn) push_to_peers<T, MODE_AB>(p, i - p.face_c0, node, f);  // compact ids: a plane is one id range
         if (node & NODE_LINKS) {
             const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : wallw;
 #pragma unroll

@@ -114,8 +114,8 @@ class SlabCase(api.Case):
         import torch
         import torch.distributed as dist
 
-        handles, _, qs, c0, boff = self.p2p_export()
-        mine = {"handles": handles, "qs": qs, "c0": c0, "boff": boff}
+        mine = self.p2p_export()
+        mine.pop("ptrs")  # raw pointers mean nothing in another process
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
         ok, attached = 1, []
@@ -124,7 +124,8 @@ class SlabCase(api.Case):
                 if 0 <= nb < self.world:
                     pa, pb = (api.p2p_open(h) + o for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]))
                     # my low face feeds the neighbour's HIGH halo plane and vice versa
-                    self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["c0"][1 - side])
+                    self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["halo_c0"][1 - side],
+                                    everyone[nb]["face_c0"][1 - side])
                     attached.append(side)
         except api.LbmError:
             ok = 0
@@ -134,7 +135,7 @@ class SlabCase(api.Case):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
             for side in attached:
-                self.p2p_attach(side, None, None, 0, 0)
+                self.p2p_attach(side, None, None)
             return False
         self._tick = torch.zeros(1, device="cuda")
         self._p2p = True

@@ -74,12 +74,14 @@ def test_aa_pulsatile_and_residual():
     assert abs(c.calc_res() - o.calc_res()) <= 1e-12 * o.calc_res()
 
 
-def test_aa_rejects_slabs():
+def test_aa_slab_needs_peer_attach():
+    """in-place storage exchanges slab faces by peer stores only"""
     import lattice_boltzmann_method_gpu_b200 as L
 
     c = H.gpu_case("ldc", 16, L.F32, L.MATH_FAST, z_range=(0, 8), storage=L.STORE_DENSE_AA)
     c.geo_pre()
     c.set_compact_offset(0, 16 ** 3)
     c.index_transform()
+    c.initialize()
     with pytest.raises(L.LbmError):
-        c.initialize()
+        c.step_begin(0)

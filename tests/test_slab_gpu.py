@@ -134,14 +134,16 @@ def test_per_slab_masks():
 
 
 @pytest.mark.parametrize("name,n,P,storage_name", [("ldc", 24, 3, "dense"), ("bif", None, 4, "dense"), ("bif", None, 4, "sparse"),
-                                                   ("cor", None, 3, "sparse"), ("ldc", 12, 12, "dense")])
+                                                   ("cor", None, 3, "sparse"), ("ldc", 12, 12, "dense"), ("ldc", 24, 3, "aa"),
+                                                   ("bif", None, 4, "aa"), ("cor", None, 5, "aa"), ("pos", 24, 2, "aa"),
+                                                   ("ldc", 12, 12, "aa")])
 def test_fused_peer_store_halo_exchange(name, n, P, storage_name):
     """lbm_p2p_attach: the step kernel stores the crossing populations straight into the neighbouring
     handle's halo plane (here: another handle on the same GPU); no pack / unpack / copy at all"""
     import lattice_boltzmann_method_gpu_b200 as L
     from lattice_boltzmann_method_gpu_b200 import slab
 
-    storage = L.STORE_SPARSE_AB if storage_name == "sparse" else L.STORE_DENSE_AB
+    storage = {"sparse": L.STORE_SPARSE_AB, "dense": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[storage_name]
     steps = 21
     one = H.gpu_case(name, n, L.F64, L.MATH_FAST, storage=storage)
     H.gpu_setup(one, name)
@@ -162,8 +164,8 @@ def test_fused_peer_store_halo_exchange(name, n, P, storage_name):
     for r, c in enumerate(cs):
         for side, nb in ((0, r - 1), (1, r + 1)):
             if 0 <= nb < P:
-                _, ptrs, qs, c0, _ = exp[nb]
-                c.p2p_attach(side, ptrs[0], ptrs[1], qs, c0[1 - side])
+                e = exp[nb]
+                c.p2p_attach(side, e["ptrs"][0], e["ptrs"][1], e["qs"], e["halo_c0"][1 - side], e["face_c0"][1 - side])
     launches0 = sum(c.launch_count for c in cs)
     for it in range(steps):
         for c in cs:

@@ -29,6 +29,8 @@ def main():
         nz = {"ldc": n, "pos": n, "bif": 32, "cor": 44}[name]
         z0, z1 = slab.slab_ranges(nz, world)[rank]
         storage = L.STORE_SPARSE_AB if os.environ.get("LBM_SPARSE") == "1" else L.STORE_DENSE_AB
+        if os.environ.get("LBM_AA") == "1":  # in-place storage: peer stores are its only transport
+            storage = L.STORE_DENSE_AA
         base = H.gpu_case(name, n, L.F64, L.MATH_FAST, z_range=(z0, z1), storage=storage)
         d = base.desc
         d.device = local
@@ -36,8 +38,8 @@ def main():
         c = slab.SlabCase(d)
         flag = H.bif_flag() if name == "bif" else (H.synthetic_openings_mask()[0] if name == "cor" else None)
         c.setup(flag=flag, bc_planes=H.bif_bc_planes() if name == "bif" else None)
-        if os.environ.get("LBM_P2P") == "1":
-            c.enable_p2p()
+        if os.environ.get("LBM_P2P") == "1" or storage == L.STORE_DENSE_AA:
+            assert c.enable_p2p(), "peer mapping unavailable"
         c.step(steps)
         mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
         counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
