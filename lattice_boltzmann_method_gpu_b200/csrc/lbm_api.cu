@@ -134,7 +134,7 @@ struct Solver final : SolverBase {
     long long n_lo_stored = 0, stored_box = 0;   // stored nodes of the low halo plane / of the whole state box
     long long sp_first = 0;                      // global compact id of the first stored node of the state box
     long long nseg = 0;
-    long long *d_cart = nullptr, *d_chunk_off = nullptr;
+    long long *d_cart = nullptr, *d_chunk_off = nullptr, *d_plane_seg = nullptr;
     uint32_t *d_nodec = nullptr;
     int8_t *d_labelc = nullptr;
     int32_t *d_rec = nullptr, *d_chunk_cnt = nullptr;
@@ -150,7 +150,7 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
-        fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt);
+        fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -492,33 +492,41 @@ struct Solver final : SolverBase {
         }
         CK(launch_compact_maps(d_index, d_node, d_wall, d_label, box.cells(), sp_first, d_cart, d_nodec, d_wallc, d_labelc, st));
         launches++;
-        // segments of the owned planes
-        const long long nchunks = (long long)nown * box.plane / 32;
-        if (!d_chunk_cnt && (dalloc(&d_chunk_cnt, (size_t)nchunks) || dalloc(&d_chunk_off, (size_t)nchunks))) return LBM_ERR_NOMEM;
-        CK(launch_build_segments(d_node, d_index, box, own_z0, own_z1, sp_first, d_chunk_cnt, d_chunk_off, d_cnt + 5, nullptr, st));
-        launches += 2;
-        CK(cudaMemcpyAsync(&nseg, d_cnt + 5, sizeof nseg, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (d_rec) cudaFree(d_rec), d_rec = nullptr;
-        if (dalloc(&d_rec, (size_t)std::max<long long>(nseg, 1) * SEG_REC)) return LBM_ERR_NOMEM;
-        CK(launch_build_segments(d_node, d_index, box, own_z0, own_z1, sp_first, d_chunk_cnt, d_chunk_off, d_cnt + 5, d_rec, st));
-        launches++;
-        {
-            // first segment of every owned plane (chunks are in plane order)
-            std::vector<long long> off((size_t)nchunks);
-            CK(cudaMemcpyAsync(off.data(), d_chunk_off, (size_t)nchunks * sizeof(long long), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const long long cpp = box.plane / 32;
-            seg_plane_start.assign((size_t)nown + 1, nseg);
-            for (int z = 0; z < nown; z++) seg_plane_start[z] = off[(size_t)z * cpp];
-        }
         // compact ranges of the halo planes and of the outermost owned planes
         const int zl_first = own_z0 - box.z0, zl_last = own_z1 - 1 - box.z0;
         halo_id0[0] = 0, halo_n[0] = lo_halo ? n_lo_stored : 0;
         face_id0[0] = n_lo_stored, face_n[0] = lo_halo ? count_plane(zl_first) : 0;
         halo_n[1] = hi_halo ? count_plane(nzl - 1) : 0, halo_id0[1] = ns - halo_n[1];
         face_n[1] = hi_halo ? count_plane(zl_last) : 0, face_id0[1] = ns - halo_n[1] - face_n[1];
-        qstride = ns + 64;
+        // segments: aligned 32-id chunks of the owned planes' compact range
+        const long long own_id0 = n_lo_stored, own_id1 = ns - halo_n[1];
+        const long long nchunks = (own_id1 - (own_id0 & ~31LL) + 31) / 32 + 1;
+        if (!d_chunk_cnt && (dalloc(&d_chunk_cnt, (size_t)nchunks) || dalloc(&d_chunk_off, (size_t)nchunks) ||
+                             dalloc(&d_plane_seg, (size_t)nown + 1)))
+            return LBM_ERR_NOMEM;
+        CK(launch_build_segments(d_nodec, d_cart, d_index, box, zl_first, own_id0, own_id1, sp_first, d_chunk_cnt, d_chunk_off,
+                                 d_cnt + 5, nullptr, nullptr, st));
+        launches += 2;
+        CK(cudaMemcpyAsync(&nseg, d_cnt + 5, sizeof nseg, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (own_id1 <= own_id0) nseg = 0;
+        if (d_rec) cudaFree(d_rec), d_rec = nullptr;
+        if (dalloc(&d_rec, (size_t)std::max<long long>(nseg, 1) * SEG_REC)) return LBM_ERR_NOMEM;
+        CK(cudaMemsetAsync(d_rec, 0, (size_t)std::max<long long>(nseg, 1) * SEG_REC * sizeof(int32_t), st));
+        CK(cudaMemsetAsync(d_plane_seg, 0x7f, ((size_t)nown + 1) * sizeof(long long), st));  // "no record yet"
+        CK(launch_build_segments(d_nodec, d_cart, d_index, box, zl_first, own_id0, own_id1, sp_first, d_chunk_cnt, d_chunk_off,
+                                 d_cnt + 5, d_rec, d_plane_seg, st));
+        launches++;
+        {
+            // first record of every owned plane (records are in plane order); planes without fluid take the next one's
+            seg_plane_start.assign((size_t)nown + 1, nseg);
+            CK(cudaMemcpyAsync(seg_plane_start.data(), d_plane_seg, (size_t)nown * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            seg_plane_start[(size_t)nown] = nseg;
+            for (int z = nown - 1; z >= 0; z--)
+                if (seg_plane_start[(size_t)z] > nseg) seg_plane_start[(size_t)z] = seg_plane_start[(size_t)z + 1];
+        }
+        qstride = (ns + 64 + 31) & ~31LL;  // every direction's array starts 256-byte aligned
         if (!d_fa) {
             const size_t fsize = (size_t)qstride * Q + 64;
             if (dalloc(&d_fa, fsize) || dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;

@@ -456,50 +456,95 @@ __global__ void k_halo_unpack(T *f, long long qstride, const int8_t *label8, int
 
 // ---------------------------------------------------------------- sparse storage
 // LBM_STORE_SPARSE_AB keeps the populations in the reference's own compact order
-// (one entry per stored node, geo != 0).  A "segment" is a run of <= 32 consecutive
-// FLUID cells of one row inside one aligned 32-cell chunk.  Every source of a fluid
-// node is a stored node (the -1 marking guarantees it) and consecutive stored x
-// positions have consecutive compact ids, so for each direction the sources of a
-// segment are one contiguous run of compact ids: a segment needs 19 base ids, not
-// 19 ids per node.  Record layout (24 x int32):
-//   [0..18] local compact id of the source of the segment's FIRST node per direction
-//           ([0] = the node itself), [19] length, [20],[21] Cartesian cell id of the
-//           first node (lo, hi), [22] 1 if any node of the run has a boundary link.
-__global__ void k_seg_count(const uint32_t *node, long long c0, long long c1, int32_t *counts) {
-    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // c0,c1 multiples of 32
-    bool fluid = c < c1 && !(node[c] & NODE_SKIP);
-    unsigned m = __ballot_sync(0xffffffffu, fluid);
-    if ((threadIdx.x & 31) == 0 && c < c1) counts[(c - c0) >> 5] = __popc(m & ~(m << 1));  // run starts
-}
-__global__ void k_seg_fill(const uint32_t *node, const int32_t *index, Box b, long long c0, long long c1,
-                           long long id_first, const long long *chunk_offset, int32_t *rec) {
-    long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// (one entry per stored node, geo != 0).  Consecutive stored x positions of a row have
+// consecutive compact ids and every source of a fluid node is a stored node (the -1
+// marking guarantees it), so for a run of fluid nodes of one row the sources of each
+// direction are one contiguous run of compact ids: 19 base ids per run, not 19 ids per
+// node.
+//
+// A warp of the step kernel owns one aligned chunk of 32 compact ids (all its loads and
+// stores of direction 0 and all its stores are 256-byte aligned rows of the SoA arrays).
+// A chunk usually holds the tail of one row's run and the head of the next one, so a
+// segment record describes up to TWO "pieces" (= run intersected with the chunk, one
+// plane); further pieces of a chunk, and pieces of another z-plane, go to further records
+// of the same chunk.  Record = 2 x 24 int32, per piece:
+//   [0..18] source compact id of direction q for LANE 0 of the chunk (source of lane l is
+//           base + l; [0] is the chunk's first id), [19] first lane | length << 8 (0 = no
+//           piece), [20],[21] Cartesian cell id of lane 0 (lo, hi), [22] 1 if any node of
+//           the piece has a boundary link, [23] unused.
+struct ChunkScan {
+    bool fluid, start;
+    long long cartc;
+    int my_rec, my_slot, nrec;
+};
+__device__ __forceinline__ ChunkScan scan_chunk(const uint32_t *nodec, const long long *cart, Box b, long long i,
+                                                long long id0, long long id1) {
     const int lane = threadIdx.x & 31;
-    uint32_t w = c < c1 ? node[c] : NODE_SKIP;
-    bool fluid = !(w & NODE_SKIP);
-    unsigned m = __ballot_sync(0xffffffffu, fluid);
-    unsigned links = __ballot_sync(0xffffffffu, fluid && (w & NODE_LINKS));
-    if (c >= c1) return;
-    unsigned starts = m & ~(m << 1);
-    if (!((starts >> lane) & 1u)) return;                 // one thread per run: its first lane
-    unsigned after = (~m) >> lane;                         // first non-fluid lane at or after me
-    int len = after ? __ffs(after) - 1 : 32 - lane;
-    unsigned runmask = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << lane;
-    long long seg = chunk_offset[(c - c0) >> 5] + __popc(starts & ((1u << lane) - 1u));
-    int32_t *r = rec + seg * 24;
+    ChunkScan r;
+    const bool valid = i >= id0 && i < id1;
+    r.fluid = valid && !(nodec[i] & NODE_SKIP);
+    r.cartc = valid ? cart[i] : -2;
+    const long long prev_c = __shfl_up_sync(0xffffffffu, r.cartc, 1);
+    const bool prev_f = __shfl_up_sync(0xffffffffu, r.fluid ? 1 : 0, 1) != 0;
+    const bool joined = lane > 0 && prev_f && prev_c == r.cartc - 1 && (r.cartc % b.px) != 0;
+    r.start = r.fluid && !joined;
+    const long long plane = r.fluid ? r.cartc / b.plane : -1;
+    unsigned remaining = __ballot_sync(0xffffffffu, r.start);
+    r.my_rec = 0, r.my_slot = 0, r.nrec = 0;
+    while (remaining) {  // one round per z-plane present in the chunk (ids are plane-ordered)
+        const int leader = __ffs(remaining) - 1;
+        const long long pl = __shfl_sync(0xffffffffu, plane, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, r.start && plane == pl);
+        if (r.start && plane == pl) {
+            const int j = __popc(grp & ((1u << lane) - 1u));
+            r.my_rec = r.nrec + (j >> 1), r.my_slot = j & 1;
+        }
+        r.nrec += (__popc(grp) + 1) >> 1;
+        remaining &= ~grp;
+    }
+    return r;
+}
+__global__ void k_seg_count(const uint32_t *nodec, const long long *cart, Box b, long long base_id, long long id0,
+                            long long id1, int32_t *counts) {
+    const long long i = base_id + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // base_id multiple of 32
+    const ChunkScan r = scan_chunk(nodec, cart, b, i, id0, id1);
+    if ((threadIdx.x & 31) == 0 && i < id1) counts[(i - base_id) >> 5] = r.nrec;
+}
+__global__ void k_seg_fill(const uint32_t *nodec, const long long *cart, const int32_t *index, Box b, int own_zl0,
+                           long long base_id, long long id0, long long id1, long long id_first,
+                           const long long *chunk_offset, int32_t *rec, long long *plane_seg) {
+    const long long i = base_id + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const ChunkScan r = scan_chunk(nodec, cart, b, i, id0, id1);
+    const unsigned cont = __ballot_sync(0xffffffffu, r.fluid && !r.start);
+    const bool has_link = r.fluid ? (nodec[i] & NODE_LINKS) != 0 : false;
+    const unsigned links = __ballot_sync(0xffffffffu, has_link);
+    if (!r.start) return;  // one thread per piece: its first lane
+    int len = 1;
+    if (lane < 31) {
+        const unsigned after = (~cont) >> (lane + 1);  // first lane after me that does not continue my run
+        len = 1 + (after ? __ffs(after) - 1 : 31 - lane);
+        if (len > 32 - lane) len = 32 - lane;
+    }
+    const unsigned piece = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << lane;
+    const long long seg = chunk_offset[(i - base_id) >> 5] + r.my_rec;
+    int32_t *o = rec + seg * SEG_REC + r.my_slot * SEG_HALF;
 #pragma unroll
     for (int q = 0; q < Q; q++) {
-        const long long s = c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
+        const long long sc = r.cartc - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
         // every source of a fluid node is stored when the mask came from geo_pre; an
         // unstored one (the reference would read d_scr[q*NLATTICE-1]) is clamped for memory safety
-        const long long id = (long long)index[s] - id_first;
-        r[q] = (int32_t)(id < 0 ? 0 : id);
+        long long id = (long long)index[sc] - id_first;
+        if (id < 0) id = 0;
+        o[q] = (int32_t)(id - lane);
     }
-    r[19] = len;
-    r[20] = (int32_t)(c & 0xffffffffLL);
-    r[21] = (int32_t)(c >> 32);
-    r[22] = (links & runmask) ? 1 : 0;
-    r[23] = 0;
+    o[19] = lane | (len << 8);
+    const long long c_lane0 = r.cartc - lane;
+    o[20] = (int32_t)(c_lane0 & 0xffffffffLL);
+    o[21] = (int32_t)(c_lane0 >> 32);
+    o[22] = (links & piece) ? 1 : 0;
+    o[23] = 0;
+    if (r.my_slot == 0) atomicMin(plane_seg + (r.cartc / b.plane - own_zl0), seg);
 }
 // exclusive scan of int32 counts into int64 offsets (single block, carry across chunks)
 __global__ void k_scan_i32(const int32_t *counts, long long *offsets, long long n, long long *total_out) {
@@ -707,17 +752,19 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
 }
 
 // ---- sparse storage
-cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Box box, int own_z0, int own_z1,
-                                  long long id_first, int32_t *counts, long long *offsets, long long *nseg_dev,
-                                  int32_t *rec, cudaStream_t s) {
-    const long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
-    const long long nchunks = (c1 - c0) >> 5;
+cudaError_t launch_build_segments(const uint32_t *nodec, const long long *cart, const int32_t *index, Box box,
+                                  int own_zl0, long long id0, long long id1, long long id_first, int32_t *counts,
+                                  long long *offsets, long long *nseg_dev, int32_t *rec, long long *plane_seg,
+                                  cudaStream_t s) {
+    const long long base_id = id0 & ~31LL;
+    const long long nchunks = (id1 - base_id + 31) >> 5;
     if (nchunks <= 0) return cudaSuccess;
-    if (!rec) {  // pass 1: count runs per chunk and scan
-        k_seg_count<<<nblocks(c1 - c0, 256), 256, 0, s>>>(node, c0, c1, counts);
+    if (!rec) {  // pass 1: records per chunk and scan
+        k_seg_count<<<nblocks(nchunks * 32, 256), 256, 0, s>>>(nodec, cart, box, base_id, id0, id1, counts);
         k_scan_i32<<<1, SCAN_BLOCK, 0, s>>>(counts, offsets, nchunks, nseg_dev);
     } else {     // pass 2: fill the records
-        k_seg_fill<<<nblocks(c1 - c0, 256), 256, 0, s>>>(node, index, box, c0, c1, id_first, offsets, rec);
+        k_seg_fill<<<nblocks(nchunks * 32, 256), 256, 0, s>>>(nodec, cart, index, box, own_zl0, base_id, id0, id1, id_first,
+                                                              offsets, rec, plane_seg);
     }
     return cudaGetLastError();
 }

@@ -136,11 +136,15 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
                                const T *buf, cudaStream_t s);
 
 // ---- sparse storage (reference compact order + run segments), lbm_geo.cu
-constexpr int SEG_REC = 24;  // int32 per segment record, see k_seg_fill
-// pass 1 (rec == nullptr): per-chunk run counts + scan (nseg to *nseg_dev); pass 2: fill the records
-cudaError_t launch_build_segments(const uint32_t *node, const int32_t *index, Box box, int own_z0, int own_z1,
-                                  long long id_first, int32_t *counts, long long *offsets, long long *nseg_dev,
-                                  int32_t *rec, cudaStream_t s);
+constexpr int SEG_REC = 48;   // int32 per segment record: two pieces of 24, see k_seg_build
+constexpr int SEG_HALF = 24;
+// Segments over the compact ids [id0, id1) of the owned planes.  pass 1 (rec == nullptr): records per
+// aligned 32-id chunk + scan (total to *nseg_dev); pass 2: fill the records and, per owned plane, the
+// index of its first record (plane_seg[z], atomicMin; preset to a large value by the caller).
+cudaError_t launch_build_segments(const uint32_t *nodec, const long long *cart, const int32_t *index, Box box,
+                                  int own_zl0, long long id0, long long id1, long long id_first, int32_t *counts,
+                                  long long *offsets, long long *nseg_dev, int32_t *rec, long long *plane_seg,
+                                  cudaStream_t s);
 cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const uint32_t *wall, const int32_t *label,
                                 long long cells, long long id_first, long long *cart, uint32_t *nodec, uint32_t *wallc,
                                 int8_t *labelc, cudaStream_t s);

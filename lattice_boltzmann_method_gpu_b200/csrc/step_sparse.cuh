@@ -2,11 +2,12 @@
 // compact order (one entry per stored node, index_transform numbering, bifurcation.cu:241-252), two
 // buffers, addressed through run-segment records instead of a per-node neighbour list.
 //
-// One warp = one segment = a run of <= 32 consecutive fluid nodes of one row.  For each direction the
-// sources of the run are one contiguous range of compact ids (every source of a fluid node is a stored
-// node, and consecutive stored x positions have consecutive ids), so the warp needs the record's 19
-// base ids (one 96-byte load, broadcast by shuffles) and then issues 19 coalesced loads -- 2.5 B of
-// index traffic per node instead of the 72 B of an 18-entry neighbour list.
+// One warp = one segment = one aligned chunk of 32 compact ids, holding up to two "pieces" (the tail
+// of one row's run of fluid nodes and the head of the next; lbm_geo.cu, k_seg_fill).  For each
+// direction the sources of a piece are one contiguous range of compact ids, so the warp needs the
+// record's 19 base ids per piece (one 192-byte load, broadcast by shuffles) and then issues 19 coalesced
+// loads -- 6 B of index traffic per node instead of the 72 B of an 18-entry neighbour list -- and 19
+// stores that are full aligned 256-byte rows (fp64) of the destination arrays.
 //
 // Boundary links work exactly as in step_dense.cuh: the slot of link q is the pull source itself,
 // dst[q][base_q + lane] -- wall, inlet/outlet and -1 nodes ARE stored nodes in this layout, as in the
@@ -26,14 +27,29 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
     const int lane = threadIdx.x & 31;
     const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
     if (seg >= sp.seg_end) return;
-    const int32_t r = lane < SEG_REC ? sp.rec[seg * SEG_REC + lane] : 0;
-    const int len = __shfl_sync(0xffffffffu, r, 19);
-    const bool active = lane < len;
+    const int32_t r0 = sp.rec[seg * SEG_REC + lane];
+    const int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
+    const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
+    const bool two = (mB >> 8) != 0;  // warp-uniform
+    const bool inB = two && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
+    const bool active = inB || (lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8));
     int base[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) base[q] = __shfl_sync(0xffffffffu, r, q);
-    const unsigned clo = (unsigned)__shfl_sync(0xffffffffu, r, 20), chi = (unsigned)__shfl_sync(0xffffffffu, r, 21);
-    const int has_links = __shfl_sync(0xffffffffu, r, 22);
+    for (int q = 0; q < Q; q++) base[q] = __shfl_sync(0xffffffffu, r0, q);
+    unsigned clo = (unsigned)__shfl_sync(0xffffffffu, r0, 20), chi = (unsigned)__shfl_sync(0xffffffffu, r0, 21);
+    int has_links = __shfl_sync(0xffffffffu, r0, 22);
+    if (two) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int bq = SEG_HALF + q < 32 ? __shfl_sync(0xffffffffu, r0, SEG_HALF + q)
+                                             : __shfl_sync(0xffffffffu, r1, SEG_HALF + q - 32);
+            if (inB) base[q] = bq;
+        }
+        const unsigned blo = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 20 - 32);
+        const unsigned bhi = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 21 - 32);
+        const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
+        if (inB) clo = blo, chi = bhi, has_links = bl;
+    }
     double velsum = 0.0;
     if (active) {
         const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
