@@ -17,6 +17,7 @@
 #include <new>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lbm_internal.h"
@@ -592,6 +593,10 @@ struct Solver final : SolverBase {
         if (sparse) {
             SparseParams<T> sp{};
             sp.base = p, sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc;
+            {
+                static const int spw_env = getenv("LBM_SPW") ? atoi(getenv("LBM_SPW")) : 0;  // tuning knob
+                sp.spw = spw_env > 0 ? spw_env : 1;   // measured: 1 is fastest (profiles/r01_notes.md)
+            }
             const long long zA = c0 / box.plane - (own_z0 - box.z0), zB = c1 / box.plane - (own_z0 - box.z0);
             sp.seg_begin = seg_plane_start[(size_t)zA], sp.seg_end = seg_plane_start[(size_t)zB];
             if (sp.seg_end <= sp.seg_begin) return 0;
@@ -965,44 +970,55 @@ struct Solver final : SolverBase {
         // The bodies: the same characters `ofs << value << ' '` produces (default ostream float format =
         // %g with 6 significant digits = std::to_chars general/6), formatted into one buffer -- at 512^3
         // the reference's ASCII writer would otherwise dominate the run.
-        std::string buf;
-        buf.reserve((size_t)(x1 - x0) * (y1 - y0) * (z1 - z0) * 3 * 12 + 64);
-        char tmp[48];
-        auto put = [&](auto v) {
+        // z-planes are formatted by several host threads into their own buffers and written in order.
+        const int nzp = z1 - z0;
+        const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, nzp}));
+        auto put = [](std::string &buf, auto v) {
+            char tmp[48];
             auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::general, 6);
             buf.append(tmp, r.ptr);
             buf.push_back(' ');
         };
+        // kind 0: density, 1: pressure, 2: velocity
+        auto format_planes = [&](int kind, std::vector<std::string> &parts) {
+            parts.assign((size_t)nthr, std::string());
+            auto work = [&](int t) {
+                const int za = z0 + (int)((long long)nzp * t / nthr), zb = z0 + (int)((long long)nzp * (t + 1) / nthr);
+                std::string &buf = parts[(size_t)t];
+                buf.reserve((size_t)(x1 - x0) * (y1 - y0) * (zb - za) * (kind == 2 ? 36 : 12) + 64);
+                for (int z = za; z < zb; z++)
+                    for (int y = y0; y < y1; y++)
+                        for (int x = x0; x < x1; x++) {
+                            const int i = idx_of(x, y, z);
+                            if (kind == 0) put(buf, i >= 0 ? (float)w_rho[i] * C_rho : 0.0f);
+                            else if (kind == 1) {
+                                if (i >= 0) put(buf, (float)w_rho[i] * C_pre / 3.0);  // double, as in cor.cu:983
+                                else put(buf, 0.0f);
+                            } else if (i >= 0) {
+                                put(buf, (float)w_ux[i] * C_U), put(buf, (float)w_uy[i] * C_U), put(buf, (float)w_uz[i] * C_U);
+                            } else {
+                                buf += "0 0 0 ";
+                            }
+                        }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthr; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+        };
+        std::vector<std::string> parts;
+        auto flush = [&]() {
+            for (auto &s : parts) ofs.write(s.data(), (std::streamsize)s.size());
+        };
         if (d.case_rule == LBM_CASE_GEO_OPENINGS) {
-            buf += "SCALARS DENSITY float\nLOOKUP_TABLE default\n";
-            for (int z = z0; z < z1; z++)
-                for (int y = y0; y < y1; y++)
-                    for (int x = x0; x < x1; x++) {
-                        int i = idx_of(x, y, z);
-                        put(i >= 0 ? (float)w_rho[i] * C_rho : 0.0f);
-                    }
-            buf += "\nSCALARS PRESSURE float\nLOOKUP_TABLE default\n";
-            for (int z = z0; z < z1; z++)
-                for (int y = y0; y < y1; y++)
-                    for (int x = x0; x < x1; x++) {
-                        int i = idx_of(x, y, z);
-                        if (i >= 0) put((float)w_rho[i] * C_pre / 3.0);  // double, as in cor.cu:983
-                        else put(0.0f);
-                    }
-            buf += "\n";
+            ofs << "SCALARS DENSITY float\nLOOKUP_TABLE default\n";
+            format_planes(0, parts), flush();
+            ofs << "\nSCALARS PRESSURE float\nLOOKUP_TABLE default\n";
+            format_planes(1, parts), flush();
+            ofs << "\n";
         }
-        buf += "VECTORS VELOCITY float\n";
-        for (int z = z0; z < z1; z++)
-            for (int y = y0; y < y1; y++)
-                for (int x = x0; x < x1; x++) {
-                    int i = idx_of(x, y, z);
-                    if (i >= 0) {
-                        put((float)w_ux[i] * C_U), put((float)w_uy[i] * C_U), put((float)w_uz[i] * C_U);
-                    } else {
-                        buf += "0 0 0 ";
-                    }
-                }
-        ofs.write(buf.data(), (std::streamsize)buf.size());
+        ofs << "VECTORS VELOCITY float\n";
+        format_planes(2, parts), flush();
         ofs.close();
         return 0;
     }

@@ -169,6 +169,7 @@ struct SparseParams {
     const uint32_t *nodec;   // node words by compact id
     const uint32_t *wallc;   // wall masks by compact id
     long long seg_begin, seg_end;
+    int spw;                 // consecutive records per warp
 };
 
 // fused step (lbm_step_fast.cu / lbm_step_strict.cu)

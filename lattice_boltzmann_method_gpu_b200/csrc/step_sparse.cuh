@@ -25,67 +25,89 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
     k_step_sparse(const __grid_constant__ SparseParams<T> sp) {
     const StepParams<T> &p = sp.base;
     const int lane = threadIdx.x & 31;
-    const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
-    if (seg >= sp.seg_end) return;
-    const int32_t r0 = sp.rec[seg * SEG_REC + lane];
-    const int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
-    const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
-    const bool two = (mB >> 8) != 0;  // warp-uniform
-    const bool inB = two && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
-    const bool active = inB || (lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8));
-    int base[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) base[q] = __shfl_sync(0xffffffffu, r0, q);
-    unsigned clo = (unsigned)__shfl_sync(0xffffffffu, r0, 20), chi = (unsigned)__shfl_sync(0xffffffffu, r0, 21);
-    int has_links = __shfl_sync(0xffffffffu, r0, 22);
-    if (two) {
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const int bq = SEG_HALF + q < 32 ? __shfl_sync(0xffffffffu, r0, SEG_HALF + q)
-                                             : __shfl_sync(0xffffffffu, r1, SEG_HALF + q - 32);
-            if (inB) base[q] = bq;
-        }
-        const unsigned blo = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 20 - 32);
-        const unsigned bhi = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 21 - 32);
-        const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
-        if (inB) clo = blo, chi = bhi, has_links = bl;
-    }
+    // a warp walks `spw` consecutive records; the next record is fetched while the current one is
+    // processed, so only the first record load of a warp is exposed in front of the 19 pulls
+    long long seg = sp.seg_begin + ((long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5)) * sp.spw;
+    const long long seg_last = (seg + sp.spw < sp.seg_end ? seg + sp.spw : sp.seg_end) - 1;
+    if (seg > seg_last) return;
+    int32_t r0 = sp.rec[seg * SEG_REC + lane];
+    int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
     double velsum = 0.0;
-    if (active) {
-        const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
-        const long long i = (long long)base[0] + lane;                                   // compact id
-        const uint32_t node = has_links ? sp.nodec[i] : 0u;
-        const uint32_t wallw = has_links ? sp.wallc[i] : 0u;
-        T f[Q];
-#pragma unroll
-        for (int q = 0; q < Q; q++) f[q] = ld_stream(p.src + (long long)q * p.qstride + base[q] + lane);
-        T rho, ux, uy, uz;
-        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-        T *dst = p.dst;
-#pragma unroll
-        for (int q = 0; q < Q; q++) dst[(long long)q * p.qstride + i] = f[q];
-        if (MOMENTS) {
-            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+    for (; seg <= seg_last; seg++) {
+        int32_t n0 = 0, n1 = 0;
+        if (seg < seg_last) {
+            n0 = sp.rec[(seg + 1) * SEG_REC + lane];
+            if (lane < SEG_REC - 32) n1 = sp.rec[(seg + 1) * SEG_REC + 32 + lane];
         }
-        if (RESID) velsum = (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
-        if (p.peer_up || p.peer_dn) push_to_peers<T, MODE_AB>(p, i - p.face_c0, node, f);  // compact ids: a plane is one id range
-        if (node & NODE_LINKS) {
-            const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : wallw;
+        const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
+        const bool two = (mB >> 8) != 0;  // warp-uniform
+        const bool inB = two && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
+        const bool active = inB || (lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8));
+        unsigned clo = (unsigned)__shfl_sync(0xffffffffu, r0, 20), chi = (unsigned)__shfl_sync(0xffffffffu, r0, 21);
+        int has_links = __shfl_sync(0xffffffffu, r0, 22);
+        if (two) {
+            const unsigned blo = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 20 - 32);
+            const unsigned bhi = (unsigned)__shfl_sync(0xffffffffu, r1, SEG_HALF + 21 - 32);
+            const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
+            if (inB) clo = blo, chi = bhi, has_links = bl;
+        }
+        const int i = __shfl_sync(0xffffffffu, r0, 0) + lane;  // compact id: the chunk's first id + lane in both pieces
+        uint32_t node = 0u, wl = 0u;
+        if (active && has_links) {
+            node = sp.nodec[i];
+            wl = sp.wallc[i];
+        }
+        // the 19 source ids are used once (they do not stay in registers next to the populations)
+        T f[Q];
+        if (!two) {  // warp-uniform: one region around all 19 pulls, not one per direction
 #pragma unroll
-            for (int q = 1; q < Q; q++)
-                if (wl & (1u << q)) dst[(long long)q * p.qstride + base[q] + lane] = f[oppq(q)];
-            const uint32_t rest = node & NODE_LINKS & ~wl;  // inlet/outlet links (slow path) or static (nothing)
-            if (rest && (node & NODE_HAS_BC)) {
+            for (int q = 0; q < Q; q++) {
+                const int bq = __shfl_sync(0xffffffffu, r0, q);
+                // idle lanes read their own (stored, unused) slot: no branch between the shuffles
+                f[q] = ld_stream(p.pull_base[q] + (active ? bq + lane : i));
+            }
+        } else {
 #pragma unroll
-                for (int q = 1; q < Q; q++) {
-                    if (rest & (1u << q)) {
-                        T h;
-                        if (boundary_link<T>(p, c, q, MODE_AB, rho, ux, uy, uz, f[q], f[oppq(q)], &h))
-                            dst[(long long)q * p.qstride + base[q] + lane] = h;
+            for (int q = 0; q < Q; q++) {
+                const int ba = __shfl_sync(0xffffffffu, r0, q);
+                const int bb = SEG_HALF + q < 32 ? __shfl_sync(0xffffffffu, r0, SEG_HALF + q)
+                                                 : __shfl_sync(0xffffffffu, r1, SEG_HALF + q - 32);
+                f[q] = ld_stream(p.pull_base[q] + (active ? (inB ? bb : ba) + lane : i));
+            }
+        }
+        T rho, ux, uy, uz;
+        if (active) {
+            collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+#pragma unroll
+            for (int q = 0; q < Q; q++) p.store_base[q][i] = f[q];
+            if (MOMENTS) {
+                p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+            }
+            if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+            if (p.peer_up || p.peer_dn) push_to_peers<T, MODE_AB>(p, (long long)i - p.face_c0, node, f);  // compact ids: a plane is one id range
+            if (node & NODE_LINKS) {
+                // boundary slots are the pull sources themselves; the few lanes that have links re-read
+                // their piece's base ids from the record (L1-resident by now)
+                const int32_t *mine = sp.rec + seg * SEG_REC + (inB ? SEG_HALF : 0);
+                wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (wl & node & NODE_LINKS);
+#pragma unroll
+                for (int q = 1; q < Q; q++)
+                    if (wl & (1u << q)) p.store_base[q][mine[q] + lane] = f[oppq(q)];
+                const uint32_t rest = (node & NODE_HAS_BC) ? (node & NODE_LINKS & ~wl) : 0u;  // inlet/outlet; static links keep their slot
+                if (rest) {
+                    const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
+#pragma unroll
+                    for (int q = 1; q < Q; q++) {
+                        if (rest & (1u << q)) {
+                            T h;
+                            if (boundary_link<T>(p, c, q, MODE_AB, rho, ux, uy, uz, f[q], f[oppq(q)], &h))
+                                p.store_base[q][mine[q] + lane] = h;
+                        }
                     }
                 }
             }
         }
+        r0 = n0, r1 = n1;
     }
     if (RESID) {
 #pragma unroll
@@ -95,9 +117,15 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
 }
 
 template <typename T, bool STRICT>
-cudaError_t launch_step_sparse_impl(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
-    const long long n = p.seg_end - p.seg_begin;
-    if (n <= 0) return cudaSuccess;
+cudaError_t launch_step_sparse_impl(const SparseParams<T> &p_in, bool moments, bool resid, cudaStream_t s) {
+    SparseParams<T> p = p_in;
+    for (int q = 0; q < Q; q++) {
+        p.base.pull_base[q] = p.base.src + (long long)q * p.base.qstride;
+        p.base.store_base[q] = p.base.dst + (long long)q * p.base.qstride;
+    }
+    const long long nrec = p.seg_end - p.seg_begin;
+    if (nrec <= 0) return cudaSuccess;
+    const long long n = (nrec + p.spw - 1) / p.spw;  // warps
     const unsigned nb = (unsigned)((n + SPARSE_BLOCK / 32 - 1) / (SPARSE_BLOCK / 32));
     if (moments && resid) k_step_sparse<T, STRICT, true, true><<<nb, SPARSE_BLOCK, 0, s>>>(p);
     else if (moments) k_step_sparse<T, STRICT, true, false><<<nb, SPARSE_BLOCK, 0, s>>>(p);

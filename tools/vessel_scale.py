@@ -2,7 +2,7 @@
 GPUs of one box (one rank per GPU, NCCL halo exchange), sparse or dense storage.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tools/vessel_scale.py [--size 1024] [--k 4] [--storage sparse|dense] [--precision f64] [--steps 50] [--verify]
+      tools/vessel_scale.py [--size 1024] [--k 4] [--storage sparse|dense|aa] [--halo p2p|nccl] [--precision f64] [--steps 50] [--verify]
 
 Each rank builds only the planes of the voxel mask it needs (lbm_set_flag_slab).  --verify recomputes
 the run as a single domain on rank 0 (small n only) and checks the gathered fields bit for bit.
@@ -38,7 +38,7 @@ def desc_for(a, z_range, device):
     d.nx = d.ny = d.nz = a.n
     d.z_begin, d.z_end = z_range
     d.precision = L.F64 if a.precision == "f64" else L.F32
-    d.storage = L.STORE_SPARSE_AB if a.storage == "sparse" else L.STORE_DENSE_AB
+    d.storage = {"sparse": L.STORE_SPARSE_AB, "dense": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[a.storage]
     d.pulse_amp, d.pulse_period = 0.3, 200.0
     d.bc[0].pulsatile = 1
     d.device = device
@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--storage", default="sparse")
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--verify", action="store_true")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -64,6 +65,9 @@ def main():
     inlet = inlet_plane(a.n, a.k, a.radius_frac)
     c.setup(flag_slab=(tube_bundle(a.n, a.k, a.radius_frac, z0, z1).astype(np.uint8), z0),
             bc_planes=(inlet, np.zeros_like(inlet)))
+    halo = "nccl"
+    if a.halo == "p2p" and world > 1:
+        halo = "p2p" if c.enable_p2p() else "nccl (peer mapping unavailable)"
     c.step(5)
     dist.barrier()
     torch.cuda.synchronize()
@@ -74,7 +78,7 @@ def main():
     dist.all_gather(per_rank, nf)
     fluid = sum(int(t[0]) for t in per_rank)
     out = {"config": f"vessel bundle {a.n}^3, {a.k}x{a.k} bent tubes, pulsatile inlet, {a.storage} storage, {a.precision}",
-           "n_gpus": world, "fluid_nodes": fluid, "fill": fluid / a.n ** 3, "nlattice": c.nlattice,
+           "n_gpus": world, "halo_exchange": halo, "fluid_nodes": fluid, "fill": fluid / a.n ** 3, "nlattice": c.nlattice,
            "mlups": fluid * a.steps / (float(ms) * 1e-3) / 1e6, "ms_per_step": float(ms) / a.steps,
            "device_GB_per_rank": [round(int(t[1]) / 1e9, 2) for t in per_rank],
            "fluid_per_rank": [int(t[0]) for t in per_rank]}
