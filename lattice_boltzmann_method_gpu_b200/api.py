@@ -368,22 +368,36 @@ class Case:
         return self._L.lbm_stream(self._h)
 
 
-_opened_ipc = {}
+_opened_ipc = {}  # handle bytes -> [mapped pointer, reference count]
 
 
 def p2p_open(handle_bytes: bytes) -> int:
     """map an allocation exported by another process (cudaIpcOpenMemHandle); an allocation can be
-    opened only once per process, so mappings are cached by handle"""
-    if handle_bytes in _opened_ipc:
-        return _opened_ipc[handle_bytes]
+    opened only once per process, so mappings are cached by handle and reference-counted"""
+    ent = _opened_ipc.get(handle_bytes)
+    if ent is not None:
+        ent[1] += 1
+        return ent[0]
     L = load_library()
     buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
     ptr = C.c_void_p()
     rc = L.lbm_p2p_open(buf, C.byref(ptr))
     if rc:
         raise LbmError(rc, L.lbm_last_error(None).decode())
-    _opened_ipc[handle_bytes] = ptr.value
+    _opened_ipc[handle_bytes] = [ptr.value, 1]
     return ptr.value
+
+
+def p2p_release(handle_bytes: bytes):
+    """drop one reference; the mapping is closed (cudaIpcCloseMemHandle) with the last one.  The
+    exporting process must not free the allocation before every importer has released it."""
+    ent = _opened_ipc.get(handle_bytes)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        del _opened_ipc[handle_bytes]
+        load_library().lbm_p2p_close(C.c_void_p(ent[0]))
 
 
 def make_case(case_rule: int, *, n=None, dims=None, precision=F32, math_mode=MATH_FAST, storage=STORE_DENSE_AB,

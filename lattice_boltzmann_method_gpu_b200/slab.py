@@ -85,6 +85,8 @@ class SlabCase(api.Case):
         self._bufs = None
         self._p2p = False
         self._tick = None
+        self._mapped = []        # IPC handles this rank holds a mapping of
+        self.p2p_error = None    # why enable_p2p fell back, if it did
 
     def setup(self, flag=None, bc_planes=None, flag_slab=None):
         """geo_pre -> (all-gather of stored counts) -> index_transform -> read_vel -> initialize"""
@@ -122,13 +124,17 @@ class SlabCase(api.Case):
         try:
             for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
                 if 0 <= nb < self.world:
-                    pa, pb = (api.p2p_open(h) + o for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]))
+                    ptrs = []
+                    for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]):
+                        ptrs.append(api.p2p_open(h) + o)
+                        self._mapped.append(h)
+                    pa, pb = ptrs
                     # my low face feeds the neighbour's HIGH halo plane and vice versa
                     self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["halo_c0"][1 - side],
                                     everyone[nb]["face_c0"][1 - side])
                     attached.append(side)
-        except api.LbmError:
-            ok = 0
+        except api.LbmError as e:
+            ok, self.p2p_error = 0, str(e)
         # all ranks or none: a rank that cannot map its neighbour (no peer access / IPC) sends everyone
         # back to the pack + NCCL path
         flag = torch.tensor([ok], device="cuda")
@@ -136,10 +142,36 @@ class SlabCase(api.Case):
         if int(flag.item()) == 0:
             for side in attached:
                 self.p2p_attach(side, None, None)
+            self._release_mappings()
             return False
         self._tick = torch.zeros(1, device="cuda")
         self._p2p = True
         return True
+
+    def _release_mappings(self):
+        for h in self._mapped:
+            api.p2p_release(h)
+        self._mapped = []
+
+    def close(self):
+        """collective when peer mappings exist: every rank unmaps its neighbours' buffers before anyone
+        frees them"""
+        if self._mapped:
+            import torch.distributed as dist
+
+            self.sync()
+            self._release_mappings()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+        self._p2p = False
+        super().close()
+
+    def __del__(self):  # never collective: a garbage-collected case only drops its own mappings
+        try:
+            self._release_mappings()
+            api.Case.close(self)
+        except Exception:
+            pass
 
     def _wrap_buffers(self):
         import torch

@@ -39,7 +39,7 @@ def main():
         flag = H.bif_flag() if name == "bif" else (H.synthetic_openings_mask()[0] if name == "cor" else None)
         c.setup(flag=flag, bc_planes=H.bif_bc_planes() if name == "bif" else None)
         if os.environ.get("LBM_P2P") == "1" or storage == L.STORE_DENSE_AA:
-            assert c.enable_p2p(), "peer mapping unavailable"
+            assert c.enable_p2p(), f"peer mapping unavailable: {c.p2p_error}"
         c.step(steps)
         mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
         counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
