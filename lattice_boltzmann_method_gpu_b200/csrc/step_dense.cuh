@@ -87,46 +87,77 @@ __device__ __forceinline__ T feq_bc_axis(T rw, int cs, T u) {
 // never written.
 enum { MODE_AB = 0, MODE_AA_EVEN = 1, MODE_AA_ODD = 2 };
 
-// Slow path of a boundary link (inlet / outlet / lid / static source): value this
-// fluid node (cell c, moments rho/u, post-collision g_q and g_opp) must leave in
-// the link's slot; `false` when nothing is to be written (static link outside the
-// odd AA step).  Only nodes next to an inlet/outlet/lid get here -- wall-only nodes
-// bounce back inline -- so it is kept out of line and the bulk path stays small.
+// Slow path of a node next to an inlet / outlet / lid (or, in the odd in-place step, next to any
+// static source): the values this fluid node (cell c, moments rho/u, post-collision populations g)
+// must leave in the slots of its links `rest`; returns the mask of links to write (a static link
+// outside the odd AA step keeps its slot).  Out of line, so the bulk path stays small, and one call
+// per NODE in three phases -- all source labels, then all prescribed speeds, then the arithmetic --
+// so that the dependent loads of the links overlap instead of queueing up link after link: these
+// few nodes set the lifetime of their CTA, which is what a small grid's step time consists of.
 template <typename T>
-__device__ __noinline__ bool boundary_link(const StepParams<T> &p, long long c, int q, int mode, T rho, T ux, T uy, T uz,
-                                           T gq, T gopp, T *out) {
+__device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long c, uint32_t rest, int mode, T rho, T ux,
+                                               T uy, T uz, const T *g, T *out) {
     const Box &b = p.box;
-    const long long s = c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q));
-    const int lab = p.label8[s];
-    if (lab == 1) {  // half-way bounce-back
-        *out = gopp;
-        return true;
-    }
-    const bool bc_link = lab >= 2 && lab < LBM_MAX_BC && p.bc[lab].kind != LBM_BC_NONE &&
-                         caxis(q, p.bc[lab].naxis) == p.bc[lab].nsign;
-    const int sx = (int)(s % b.px), sy = (int)((s / b.px) % b.ny), sz = (int)(s / b.plane) + b.z0;
-    if (!bc_link) {
-        // static link: the initial population of s, feq_q(1, u0(s))
-        if (mode != MODE_AA_ODD) return false;
-        T u0x, u0y, u0z;
-        init_velocity<T>(p.case_rule, p.u_init, p.bc, p.plane_in, p.plane_out, b, lab, sx, sy, sz, u0x, u0y, u0z);
-        *out = init_feq_q<T>(p.case_rule, q, T(1.0), u0x, u0y, u0z);
-        return true;
-    }
-    const BcEntry &e = p.bc[lab];
-    const T wden = q < 7 ? T(18.0) : T(36.0);
-    const T feq = feq_lit<T>(q, rho / T(3.0), rho / T(18.0), rho / T(36.0), ux, uy, uz);
-    T tmp;
-    if (e.kind == LBM_BC_P) {
-        const T one = T(1.0);
-        tmp = feq_lit<T>(q, one / T(3.0), one / T(18.0), one / T(36.0), ux, uy, uz);
+    int x, y, zl;  // coordinates of the node, once (32-bit arithmetic when the cell id allows it)
+    if (c < 0x7fffffffLL) {
+        const unsigned cu = (unsigned)c, px = (unsigned)b.px, ny = (unsigned)b.ny, t = cu / px;
+        x = (int)(cu - t * px), zl = (int)(t / ny), y = (int)(t - (unsigned)zl * ny);
     } else {
-        const T u = bc_speed<T>(p, e, sx, sz);
-        const T rw = e.kind == LBM_BC_V ? rho / wden : T(1.0) / wden;
-        tmp = feq_bc_axis<T>(rw, caxis(q, e.vaxis), u);
+        const long long t = c / b.px;
+        x = (int)(c - t * b.px), zl = (int)(t / b.ny), y = (int)(t - (long long)zl * b.ny);
     }
-    *out = tmp + (gq - feq) * p.om1;
-    return true;
+    int lab[Q];
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        lab[q] = 0;
+        if (rest & (1u << q)) lab[q] = p.label8[c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q))];
+    }
+    uint32_t bcm = 0;  // links whose source is an inlet/outlet node prescribing this direction
+    T ubc[Q];
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        ubc[q] = T(0.0);
+        const int l = lab[q];
+        if ((rest & (1u << q)) && l >= 2 && l < LBM_MAX_BC && p.bc[l].kind != LBM_BC_NONE &&
+            caxis(q, p.bc[l].naxis) == p.bc[l].nsign) {
+            bcm |= 1u << q;
+            // the speed is sampled at the boundary node s = x - c_q itself (pos.cu:597)
+            if (p.bc[l].kind != LBM_BC_P) ubc[q] = bc_speed<T>(p, p.bc[l], x - cxq(q), zl - czq(q) + b.z0);
+        }
+    }
+    const T r3 = rho / T(3.0), r18 = rho / T(18.0), r36 = rho / T(36.0);
+    const T one = T(1.0);
+    uint32_t wm = 0;
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        if (!(rest & (1u << q))) continue;
+        const int l = lab[q];
+        if (l == 1) {  // half-way bounce-back
+            out[q] = g[oppq(q)];
+            wm |= 1u << q;
+        } else if (bcm & (1u << q)) {
+            // feq_q(rho_bc, u_bc(s)) + (g_q(x) - feq_q(rho_x, u_x)) (1 - 1/tau)      (bif:877-1021)
+            const BcEntry &e = p.bc[l];
+            const T feq = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+            T tmp;
+            if (e.kind == LBM_BC_P) {
+                tmp = feq_lit<T>(q, one / T(3.0), one / T(18.0), one / T(36.0), ux, uy, uz);
+            } else {
+                const T rw = e.kind == LBM_BC_V ? (q < 7 ? r18 : r36) : (q < 7 ? one / T(18.0) : one / T(36.0));
+                tmp = feq_bc_axis<T>(rw, caxis(q, e.vaxis), ubc[q]);
+            }
+            out[q] = tmp + (g[q] - feq) * p.om1;
+            wm |= 1u << q;
+        } else if (mode == MODE_AA_ODD) {
+            // static link: the initial population of s, feq_q(1, u0(s))
+            T u0x, u0y, u0z;
+            init_velocity<T>(p.case_rule, p.u_init, p.bc, p.plane_in, p.plane_out, b, l, x - cxq(q), y - cyq(q),
+                             zl - czq(q) + b.z0, u0x, u0y, u0z);
+            out[q] = init_feq_q<T>(p.case_rule, q, T(1.0), u0x, u0y, u0z);
+            wm |= 1u << q;
+        }
+    }
+    return wm;
 }
 
 // ---------------------------------------------------------------------------
@@ -264,14 +295,15 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
         // rewritten -- except by the odd in-place step, which has to restore it
         const uint32_t rest = node & NODE_LINKS & ~wl;
         if (rest && ((node & NODE_HAS_BC) || MODE == MODE_AA_ODD)) {
+            T gl[Q], hv[Q];  // copies in local memory on this path only: f[] itself stays in registers
+#pragma unroll
+            for (int q = 0; q < Q; q++) gl[q] = f[q];
+            const uint32_t wm = boundary_node<T>(p, c, rest, MODE, rho, ux, uy, uz, gl, hv);
 #pragma unroll
             for (int q = 1; q < Q; q++) {
-                if (rest & (1u << q)) {
-                    T h;
-                    if (boundary_link<T>(p, c, q, MODE, rho, ux, uy, uz, f[q], f[oppq(q)], &h)) {
-                        const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                        dst[slot_index<MODE>(q, c, p.qstride, off)] = h;
-                    }
+                if (wm & (1u << q)) {
+                    const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
+                    dst[slot_index<MODE>(q, c, p.qstride, off)] = hv[q];
                 }
             }
         }

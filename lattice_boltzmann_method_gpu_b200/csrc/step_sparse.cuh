@@ -96,14 +96,13 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
                 const uint32_t rest = (node & NODE_HAS_BC) ? (node & NODE_LINKS & ~wl) : 0u;  // inlet/outlet; static links keep their slot
                 if (rest) {
                     const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
+                    T gl[Q], hv[Q];
 #pragma unroll
-                    for (int q = 1; q < Q; q++) {
-                        if (rest & (1u << q)) {
-                            T h;
-                            if (boundary_link<T>(p, c, q, MODE_AB, rho, ux, uy, uz, f[q], f[oppq(q)], &h))
-                                p.store_base[q][mine[q] + lane] = h;
-                        }
-                    }
+                    for (int q = 0; q < Q; q++) gl[q] = f[q];
+                    const uint32_t wm = boundary_node<T>(p, c, rest, MODE_AB, rho, ux, uy, uz, gl, hv);
+#pragma unroll
+                    for (int q = 1; q < Q; q++)
+                        if (wm & (1u << q)) p.store_base[q][mine[q] + lane] = hv[q];
                 }
             }
         }
