@@ -174,14 +174,20 @@ __device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long
 //                  cavities), where the wasted reads are a few percent.
 // The kernel is latency-bound per warp, so resident warps matter more than
 // anything else: CTA shape and register cap are picked per precision
-// (fp64: 128 threads x 5 CTAs/SM, 96 registers; fp32: 128 x 8, 64 registers).
+// (fp64: 128 threads x 6 CTAs/SM, 80 registers; fp32: 128 x 10, 48 registers; no spills).
 // Measurements behind every choice here: profiles/r01_notes.md.
 __host__ __device__ constexpr int cfg_block(int cfg) {
     constexpr int b[4] = {256, 256, 128, 128};
     return b[cfg];
 }
+#ifndef LBM_F32_MINB
+#define LBM_F32_MINB 10
+#endif
+#ifndef LBM_F64_MINB
+#define LBM_F64_MINB 6
+#endif
 __host__ __device__ constexpr int cfg_minb(int cfg) {
-    constexpr int m[4] = {2, 3, 5, 8};
+    constexpr int m[4] = {2, 3, LBM_F64_MINB, LBM_F32_MINB};
     return m[cfg];
 }
 template <typename T>
