@@ -19,9 +19,15 @@
 namespace lbm {
 
 constexpr int SPARSE_BLOCK = 128;
+#ifndef LBM_SP64_MINB
+#define LBM_SP64_MINB 5
+#endif
+#ifndef LBM_SP32_MINB
+#define LBM_SP32_MINB 8
+#endif
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID>
-__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? 5 : 8)
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB : LBM_SP32_MINB)
     k_step_sparse(const __grid_constant__ SparseParams<T> sp) {
     const StepParams<T> &p = sp.base;
     const int lane = threadIdx.x & 31;
