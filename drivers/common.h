@@ -20,6 +20,7 @@
 
 /* optional overrides; the reference has none (argc/argv unused, ldc.cu:612):
  *   --n N | --dims NX NY NZ | --f64 | --strict | --steps K | --save S | --tau T | --out DIR | --device D */
+static int g_out_format = LBM_OUT_ASCII_VTK; /* --binary: legacy-VTK BINARY dumps instead of the reference's ASCII */
 static int parse_common(int argc, char **argv, lbm_case_desc *d, int *steps, int *save) {
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--n") && i + 1 < argc) {
@@ -30,6 +31,7 @@ static int parse_common(int argc, char **argv, lbm_case_desc *d, int *steps, int
             d->z_begin = 0, d->z_end = d->nz;
         } else if (!strcmp(argv[i], "--f64")) d->precision = LBM_F64;
         else if (!strcmp(argv[i], "--strict")) d->math = LBM_MATH_STRICT;
+        else if (!strcmp(argv[i], "--binary")) g_out_format = LBM_OUT_BINARY_VTK;
         else if (!strcmp(argv[i], "--steps") && i + 1 < argc) *steps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--save") && i + 1 < argc) *save = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--tau") && i + 1 < argc) d->tau = atof(argv[++i]);

@@ -9,6 +9,7 @@ int main(int argc, char **argv) {
     lbm_case_defaults(LBM_CASE_GEO_OPENINGS, &d);
     if (parse_common(argc, argv, &d, &repeat, &time_save)) return 2;
     CHECK(h, lbm_create(&d, &h));
+    CHECK(h, lbm_set_output_format(h, g_out_format));
     int64_t nlattice = 0;
     CHECK(h, lbm_geo_pre(h));
     CHECK(h, lbm_index_transform(h, &nlattice));

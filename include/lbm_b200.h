@@ -211,6 +211,15 @@ int64_t lbm_device_bytes(lbm_handle h);
  * byte-compatible ASCII legacy VTK under out_dir.  Single-domain handles only. */
 int lbm_output_save(lbm_handle h, int32_t t);
 
+/* Output format of lbm_output_save and of the run loops (at 512^3 the ASCII writer
+ * dominates wall time).  LBM_OUT_ASCII_VTK (default) is the reference's format, byte for byte.
+ * LBM_OUT_BINARY_VTK writes the same points, fields and unit conversions as legacy-VTK BINARY
+ * (big-endian float32) to <out_dir>/<out_name>_<t>_bin.vtk; a z-slab handle writes its own planes
+ * to <out_name>_<t>_bin.z<first plane>.vtk with ORIGIN shifted accordingly, so the ranks of a
+ * multi-GPU run write in parallel and the pieces tile the single-domain file. */
+enum { LBM_OUT_ASCII_VTK = 0, LBM_OUT_BINARY_VTK = 1 };
+int lbm_set_output_format(lbm_handle h, int32_t format);
+
 /* The reference main loops, including CONVERGENCE.log and the stdout lines:
  *  fixed:    for i in 0..repeat inclusive, save every time_save      (bif:1246-1274, cor:1100-1132)
  *  converge: while k<=max_it && tol_count<=stag_max, residual each step (ldc:653-685, pos:986-1019) */

@@ -31,6 +31,7 @@ MATH_FAST, MATH_STRICT = 0, 1
 BC_NONE, BC_V, BC_P, BC_VP = 0, 1, 2, 3
 SRC_CONST, SRC_PARABOLA, SRC_PLANE_INLET, SRC_PLANE_OUTLET = 0, 1, 2, 3
 RES_VELSUM, RES_U2SUM = 0, 1
+OUT_ASCII_VTK, OUT_BINARY_VTK = 0, 1
 STEP_MOMENTS, STEP_VELSUM = 1, 2
 MAX_BC, MAX_OPENINGS = 8, 8
 
@@ -75,7 +76,7 @@ ABI_SYMBOLS = [
     "lbm_index_transform", "lbm_local_stored_count", "lbm_set_compact_offset", "lbm_read_vel", "lbm_set_bc_planes",
     "lbm_initialize", "lbm_step", "lbm_step_timed", "lbm_step_count", "lbm_launch_count", "lbm_residual",
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
-    "lbm_device_bytes", "lbm_output_save", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
+    "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
     "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
 ]
@@ -121,6 +122,7 @@ def load_library() -> C.CDLL:
         "lbm_num_fluid": ([vp], i64),
         "lbm_device_bytes": ([vp], i64),
         "lbm_output_save": ([vp, i32], C.c_int),
+        "lbm_set_output_format": ([vp, i32], C.c_int),
         "lbm_run_fixed": ([vp, i32, i32, i32], C.c_int),
         "lbm_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
         "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t), P(C.c_size_t)], C.c_int),
@@ -328,6 +330,10 @@ class Case:
 
     def outputSave(self, t: int):
         self._ck(self._L.lbm_output_save(self._h, int(t)))
+
+    def set_output_format(self, fmt: int):
+        """OUT_ASCII_VTK (the reference's files, default) or OUT_BINARY_VTK (legacy-VTK BINARY; also for slabs)"""
+        self._ck(self._L.lbm_set_output_format(self._h, int(fmt)))
 
     def run_fixed(self, repeat: int, time_save: int, write_files: bool = True):
         self._ck(self._L.lbm_run_fixed(self._h, repeat, time_save, int(write_files)))

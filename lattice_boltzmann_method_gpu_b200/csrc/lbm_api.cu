@@ -59,6 +59,7 @@ struct SolverBase {
     virtual int get_fields(void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count) = 0;
     virtual int get_populations(void *f) = 0;
     virtual int output_save(int t) = 0;
+    int out_format = LBM_OUT_ASCII_VTK;
     virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
                              double *res) = 0;
@@ -931,9 +932,10 @@ struct Solver final : SolverBase {
     std::vector<int32_t> w_index;
     std::vector<T> w_rho, w_ux, w_uy, w_uz;
     int fetch_for_output() {
-        if (lo_halo || hi_halo) FAIL(LBM_ERR_STATE, "writers need a single-domain handle");
+        if ((lo_halo || hi_halo) && out_format == LBM_OUT_ASCII_VTK)
+            FAIL(LBM_ERR_STATE, "the ASCII writer needs a single-domain handle (slabs: LBM_OUT_BINARY_VTK)");
         if (w_index.empty()) {
-            w_index.resize((size_t)d.nx * d.ny * d.nz);
+            w_index.resize((size_t)d.nx * d.ny * (size_t)(own_z1 - own_z0));
             int r = get_index(w_index.data());
             if (r) return r;
         }
@@ -944,9 +946,91 @@ struct Solver final : SolverBase {
 
     // outputSave: ldc.cu:582-610, pos:903-938, bif:1095-1156, cor:948-1011.
     // Same loops, same `ofstream <<` formatting of float values.
+    // Legacy-VTK BINARY: same header, points, fields and unit factors as the ASCII writer, values as
+    // big-endian float32.  A slab handle writes its own planes (ORIGIN shifted in z).
+    int output_save_binary(int t) {
+        const int NX = d.nx, NY = d.ny, NZ = d.nz;
+        const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
+        const float C_pre = C_rho * C_U * C_U;
+        const bool ldc = d.case_rule == LBM_CASE_LDC;
+        const int x0 = ldc ? 2 : 1, x1 = ldc ? NX - 2 : NX - 1, y0 = 2, y1 = NY - 2, zt0 = ldc ? 2 : 1,
+                  zt1 = ldc ? NZ - 2 : NZ - 1;
+        const int z0 = std::max(zt0, own_z0), z1 = std::min(zt1, own_z1);
+        const bool piece = lo_halo || hi_halo;
+        std::string path = std::string(d.out_dir) + "/" + d.out_name + "_" + std::to_string(t) + "_bin";
+        if (piece) path += ".z" + std::to_string(own_z0);
+        path += ".vtk";
+        const long long npts = z1 > z0 ? (long long)(x1 - x0) * (y1 - y0) * (z1 - z0) : 0;
+        std::ofstream ofs(path, std::ios::binary);
+        if (!ofs) FAIL(LBM_ERR_IO, "cannot write '%s'", path.c_str());
+        ofs << "# vtk DataFile Version 2.0\n";
+        ofs << "<-- LBM flow with UIV acceleration, http://www.bg.ic.ac.uk/research/m.tang/ulis/ -->\n";
+        ofs << "BINARY\nDATASET STRUCTURED_POINTS\n";
+        ofs << "DIMENSIONS " << (x1 - x0) << ' ' << (y1 - y0) << ' ' << std::max(0, z1 - z0) << "\n";
+        ofs << "SPACING " << CH << ' ' << CH << ' ' << CH << "\n";
+        const float oz = (float)(std::max(z0, zt0) - zt0) * CH;
+        if (ldc) ofs << "ORIGIN " << std::round(NX / 2 - 1) * CH << ' ' << std::round(NY / 2 - 1) * CH << ' ' << oz << "\n";
+        else ofs << "ORIGIN " << std::round(NX / 2) * CH << ' ' << std::round(NY / 2) * CH << ' ' << oz << "\n";
+        ofs << "POINT_DATA  " << npts << "\n";
+        if (npts == 0) return 0;
+        auto be = [](float v) {
+            uint32_t u;
+            memcpy(&u, &v, 4);
+            return __builtin_bswap32(u);
+        };
+        // w_index holds the owned planes only; field arrays start at this handle's first compact id
+        auto idx_of = [&](int x, int y, int z) {
+            const int g = w_index[(size_t)x + (size_t)NX * ((size_t)y + (size_t)NY * (size_t)(z - own_z0))];
+            return g < 0 ? (long long)-1 : (long long)g - compact_first;
+        };
+        const int nzp = z1 - z0;
+        const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, nzp}));
+        std::vector<uint32_t> buf;
+        // kind 0: density, 1: pressure, 2: velocity
+        auto section = [&](int kind) {
+            const int ncomp = kind == 2 ? 3 : 1;
+            buf.resize((size_t)npts * ncomp);
+            auto work = [&](int th) {
+                const int za = z0 + (int)((long long)nzp * th / nthr), zb = z0 + (int)((long long)nzp * (th + 1) / nthr);
+                size_t o = (size_t)(za - z0) * (y1 - y0) * (x1 - x0) * ncomp;
+                for (int z = za; z < zb; z++)
+                    for (int y = y0; y < y1; y++)
+                        for (int x = x0; x < x1; x++) {
+                            const long long i = idx_of(x, y, z);
+                            if (kind == 0) buf[o++] = be(i >= 0 ? (float)w_rho[i] * C_rho : 0.0f);
+                            else if (kind == 1) buf[o++] = be(i >= 0 ? (float)((float)w_rho[i] * C_pre / 3.0) : 0.0f);
+                            else {
+                                buf[o++] = be(i >= 0 ? (float)w_ux[i] * C_U : 0.0f);
+                                buf[o++] = be(i >= 0 ? (float)w_uy[i] * C_U : 0.0f);
+                                buf[o++] = be(i >= 0 ? (float)w_uz[i] * C_U : 0.0f);
+                            }
+                        }
+            };
+            std::vector<std::thread> pool;
+            for (int th = 1; th < nthr; th++) pool.emplace_back(work, th);
+            work(0);
+            for (auto &thd : pool) thd.join();
+            ofs.write((const char *)buf.data(), (std::streamsize)(buf.size() * sizeof(uint32_t)));
+        };
+        if (d.case_rule == LBM_CASE_GEO_OPENINGS) {
+            ofs << "SCALARS DENSITY float\nLOOKUP_TABLE default\n";
+            section(0);
+            ofs << "\nSCALARS PRESSURE float\nLOOKUP_TABLE default\n";
+            section(1);
+            ofs << "\n";
+        }
+        ofs << "VECTORS VELOCITY float\n";
+        section(2);
+        ofs << "\n";
+        ofs.close();
+        if (!ofs) FAIL(LBM_ERR_IO, "short write to '%s'", path.c_str());
+        return 0;
+    }
+
     int output_save(int t) override {
         int r = fetch_for_output();
         if (r) return r;
+        if (out_format == LBM_OUT_BINARY_VTK) return output_save_binary(t);
         const int NX = d.nx, NY = d.ny, NZ = d.nz;
         const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
         const float C_pre = C_rho * C_U * C_U;
@@ -1335,6 +1419,15 @@ int lbm_debug_get_populations(lbm_handle h, void *f) { H_OR_FAIL; return f ? h->
 int64_t lbm_num_fluid(lbm_handle h) { return h ? h->s->nfluid : -1; }
 int64_t lbm_device_bytes(lbm_handle h) { return h ? h->s->dev_bytes : -1; }
 int lbm_output_save(lbm_handle h, int32_t t) { H_OR_FAIL; return h->s->output_save(t); }
+int lbm_set_output_format(lbm_handle h, int32_t format) {
+    H_OR_FAIL;
+    if (format != LBM_OUT_ASCII_VTK && format != LBM_OUT_BINARY_VTK) {
+        h->s->err = "unknown output format";
+        return LBM_ERR_ARG;
+    }
+    h->s->out_format = format;
+    return 0;
+}
 int lbm_run_fixed(lbm_handle h, int32_t repeat, int32_t time_save, int32_t wf) { H_OR_FAIL; return h->s->run_fixed(repeat, time_save, wf); }
 int lbm_run_converge(lbm_handle h, int32_t max_it, double tol, int32_t stag_max, int32_t time_save, int32_t wf,
                      int32_t *its, double *res) {

@@ -93,7 +93,7 @@ def oracle_case(name, n=None, dtype=np.float32, pulse=None, shipped_bc=False):
 
 
 def gpu_case(name, n=None, precision=None, math_mode=None, pulse=None, shipped_bc=False, z_range=None,
-             storage=None):
+             storage=None, out_dir=None):
     """The same case on the CUDA library, driven through the reference-named call sequence."""
     import lattice_boltzmann_method_gpu_b200 as L
 
@@ -124,6 +124,8 @@ def gpu_case(name, n=None, precision=None, math_mode=None, pulse=None, shipped_b
         raise ValueError(name)
     d.z_begin, d.z_end = (0, d.nz) if z_range is None else z_range
     d.precision, d.math, d.storage = precision, math_mode, storage
+    if out_dir is not None:
+        d.out_dir = str(out_dir).encode()
     if pulse:
         d.pulse_amp, d.pulse_period = pulse
         for i in range(d.n_bc):
@@ -154,3 +156,27 @@ def rel_err(got, ref):
     e_u = max(float(np.abs(g.astype(np.float64) - r.astype(np.float64)).max()) for g, r in zip(got[1:], ref[1:]))
     e_r = float(np.abs(got[0].astype(np.float64) - ref[0].astype(np.float64)).max())
     return max(e_u / scale, e_r)
+
+
+def attach_virtual_slabs(cs):
+    """several slab handles on ONE GPU: every handle stores its crossing populations straight into its
+    neighbours' buffers (lbm_p2p_attach with plain device pointers)"""
+    exp = [c.p2p_export() for c in cs]
+    for r, c in enumerate(cs):
+        for side, nb in ((0, r - 1), (1, r + 1)):
+            if 0 <= nb < len(cs):
+                e = exp[nb]
+                c.p2p_attach(side, e["ptrs"][0], e["ptrs"][1], e["qs"], e["halo_c0"][1 - side], e["face_c0"][1 - side])
+
+
+def step_virtual_slabs(cs, steps):
+    """lock-step stepping of attached virtual slabs; moments are materialised on the last step"""
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    for it in range(steps):
+        for c in cs:
+            c.step_begin(L.STEP_MOMENTS if it == steps - 1 else 0)
+            c.step_interior()
+            c.step_end()
+        for c in cs:
+            c.sync()
