@@ -286,6 +286,26 @@ int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64
 void *lbm_stream(lbm_handle h);
 int lbm_sync(lbm_handle h);
 
+/* ---- geometry front end: STL surface -> binary voxel field (what geo.txt holds before geo_pre).
+ * Replaces the MATLAB pre-processing step the reference does not ship (bifurcation/README.md:1-5:
+ * bif.stl -> geo.txt).  Voxel (i,j,k) has its centre at origin + (i+.5, j+.5, k+.5) * spacing; a voxel
+ * is inside when the +x ray from -inf to its centre crosses the surface an odd number of times, so
+ * the surface must be closed around x (open vessel ends along y or z are fine).  flag_out receives
+ * planes [z_begin, z_end) as [z][y][x] bytes (1 inside) -- the layout lbm_set_flag_slab takes, so every
+ * rank of a z-slab run voxelises only its own planes.  Deterministic (order-independent XOR marking). */
+typedef struct lbm_voxel_grid {
+    double origin[3];
+    double spacing;
+    int32_t nx, ny, nz;
+    int32_t reserved;
+} lbm_voxel_grid;
+int lbm_voxelize_stl(const char *stl_path, const lbm_voxel_grid *grid, int32_t z_begin, int32_t z_end, int32_t device,
+                     uint8_t *flag_out);
+/* same from memory: tri = [ntri][3 vertices][x,y,z] floats */
+int lbm_voxelize_triangles(const float *tri, int64_t ntri, const lbm_voxel_grid *grid, int32_t z_begin, int32_t z_end,
+                           int32_t device, uint8_t *flag_out);
+const char *lbm_voxel_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,12 +76,18 @@ ABI_SYMBOLS = [
     "lbm_index_transform", "lbm_local_stored_count", "lbm_set_compact_offset", "lbm_read_vel", "lbm_set_bc_planes",
     "lbm_initialize", "lbm_step", "lbm_step_timed", "lbm_step_count", "lbm_launch_count", "lbm_residual",
     "lbm_get_geo", "lbm_get_index", "lbm_get_fields", "lbm_debug_get_populations", "lbm_num_fluid",
-    "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
+    "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_voxelize_stl", "lbm_voxelize_triangles", "lbm_voxel_last_error", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
     "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
 ]
 
 _lib = None
+
+
+class VoxelGrid(C.Structure):
+    """lbm_voxel_grid (include/lbm_b200.h)"""
+    _fields_ = [("origin", C.c_double * 3), ("spacing", C.c_double), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("nz", C.c_int32), ("reserved", C.c_int32)]
 
 
 def load_library() -> C.CDLL:
@@ -123,6 +129,9 @@ def load_library() -> C.CDLL:
         "lbm_device_bytes": ([vp], i64),
         "lbm_output_save": ([vp, i32], C.c_int),
         "lbm_set_output_format": ([vp, i32], C.c_int),
+        "lbm_voxelize_stl": ([C.c_char_p, P(VoxelGrid), i32, i32, i32, vp], C.c_int),
+        "lbm_voxelize_triangles": ([vp, i64, P(VoxelGrid), i32, i32, i32, vp], C.c_int),
+        "lbm_voxel_last_error": ([], C.c_char_p),
         "lbm_run_fixed": ([vp, i32, i32, i32], C.c_int),
         "lbm_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
         "lbm_halo_buffers": ([vp, i32, P(vp), P(vp), P(C.c_size_t), P(C.c_size_t)], C.c_int),
@@ -404,6 +413,26 @@ def p2p_release(handle_bytes: bytes):
     if ent[1] <= 0:
         del _opened_ipc[handle_bytes]
         load_library().lbm_p2p_close(C.c_void_p(ent[0]))
+
+
+def voxelize(surface, origin, spacing: float, dims, z_range=None, device: int = 0) -> np.ndarray:
+    """STL file (path) or triangle array [n][3][3] -> uint8 mask [z1-z0][ny][nx] (1 inside), the binary
+    voxel field geo.txt holds; dims = (nx, ny, nz).  Runs on the GPU (csrc/lbm_voxel.cu)."""
+    L = load_library()
+    g = VoxelGrid()
+    g.origin[:] = [float(v) for v in origin]
+    g.spacing = float(spacing)
+    g.nx, g.ny, g.nz = (int(v) for v in dims)
+    z0, z1 = (0, g.nz) if z_range is None else (int(z_range[0]), int(z_range[1]))
+    out = np.zeros((max(z1 - z0, 0), g.ny, g.nx), dtype=np.uint8)
+    if isinstance(surface, (str, os.PathLike)):
+        rc = L.lbm_voxelize_stl(os.fsencode(str(surface)), C.byref(g), z0, z1, device, out.ctypes.data)
+    else:
+        tri = np.ascontiguousarray(surface, dtype=np.float32).reshape(-1, 9)
+        rc = L.lbm_voxelize_triangles(tri.ctypes.data, tri.shape[0], C.byref(g), z0, z1, device, out.ctypes.data)
+    if rc:
+        raise LbmError(rc, L.lbm_voxel_last_error().decode())
+    return out
 
 
 def make_case(case_rule: int, *, n=None, dims=None, precision=F32, math_mode=MATH_FAST, storage=STORE_DENSE_AB,

@@ -39,7 +39,8 @@ def cor_reference_rules(nx: int, ny: int, nz: int) -> np.ndarray:
 
 def build(force: bool = False) -> Path:
     """Compile the oracle (and oracle/_ref when /root/reference exists)."""
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < (HERE / "lbm_oracle.c").stat().st_mtime:
+    newest = max((HERE / f).stat().st_mtime for f in ("lbm_oracle.c", "voxel_oracle.c"))
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(HERE), "liblbm_oracle.so"], check=True, capture_output=True)
     return LIB_PATH
 
@@ -228,3 +229,37 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------- STL voxeliser (voxel_oracle.c)
+class VoxGrid(C.Structure):
+    _fields_ = [("origin", C.c_double * 3), ("spacing", C.c_double), ("nx", C.c_int32), ("ny", C.c_int32),
+                ("nz", C.c_int32), ("reserved", C.c_int32)]
+
+
+def read_stl(path) -> np.ndarray:
+    """binary STL -> float32 [ntri][3][3]"""
+    raw = Path(path).read_bytes()
+    n = int(np.frombuffer(raw, dtype="<u4", count=1, offset=80)[0])
+    if 84 + 50 * n != len(raw):
+        raise ValueError(f"{path}: not a binary STL")
+    rec = np.frombuffer(raw, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n, offset=84)
+    return np.ascontiguousarray(rec["v"], dtype=np.float32)
+
+
+def voxelize(tri: np.ndarray, origin, spacing: float, dims, z_range=None) -> np.ndarray:
+    """uint8 [z1-z0][ny][nx], 1 inside; dims = (nx, ny, nz)"""
+    L = lib()
+    tri = np.ascontiguousarray(tri, dtype=np.float32).reshape(-1, 9)
+    g = VoxGrid()
+    g.origin[:] = [float(v) for v in origin]
+    g.spacing = float(spacing)
+    g.nx, g.ny, g.nz = (int(v) for v in dims)
+    z0, z1 = (0, g.nz) if z_range is None else z_range
+    out = np.zeros((z1 - z0, g.ny, g.nx), dtype=np.uint8)
+    L.vox_oracle.restype = C.c_int
+    L.vox_oracle.argtypes = [C.c_void_p, C.c_int64, C.POINTER(VoxGrid), C.c_int32, C.c_int32, C.c_void_p]
+    rc = L.vox_oracle(tri.ctypes.data, tri.shape[0], C.byref(g), z0, z1, out.ctypes.data)
+    if rc:
+        raise MemoryError("vox_oracle")
+    return out

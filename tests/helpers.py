@@ -180,3 +180,71 @@ def step_virtual_slabs(cs, steps):
             c.step_end()
         for c in cs:
             c.sync()
+
+
+# ---------------------------------------------------------------- triangle meshes for the voxeliser tests
+def mesh_box(lo, hi):
+    """12 triangles; every face is split along a diagonal (rays through voxel centres hit those edges)"""
+    lo, hi = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+    c = np.array([[lo[0] if not (i & 1) else hi[0], lo[1] if not (i & 2) else hi[1], lo[2] if not (i & 4) else hi[2]]
+                  for i in range(8)], dtype=np.float32)
+    quads = [(0, 2, 6, 4), (1, 5, 7, 3), (0, 4, 5, 1), (2, 3, 7, 6), (0, 1, 3, 2), (4, 6, 7, 5)]
+    tris = []
+    for a, b, cc, d in quads:
+        tris += [[c[a], c[b], c[cc]], [c[a], c[cc], c[d]]]
+    return np.array(tris, dtype=np.float32)
+
+
+def mesh_sphere(center, r, nu=48, nv=24):
+    """closed UV sphere"""
+    center = np.asarray(center, dtype=np.float64)
+    th = np.linspace(0.0, np.pi, nv + 1)
+    ph = np.linspace(0.0, 2 * np.pi, nu + 1)
+    P = np.array([[center + r * np.array([np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)]) for p in ph[:-1]]
+                  for t in th])
+    P[0, :] = center + [0, 0, r]      # exact, shared poles: the fan triangles meet in one vertex
+    P[-1, :] = center + [0, 0, -r]
+    tris = []
+    for i in range(nv):
+        for j in range(nu):
+            a, b, c, d = P[i, j], P[i, (j + 1) % nu], P[i + 1, (j + 1) % nu], P[i + 1, j]
+            if i > 0:
+                tris.append([a, b, c])
+            if i < nv - 1:
+                tris.append([a, c, d])
+    return np.array(tris, dtype=np.float32)
+
+
+def mesh_tube(length, r, bend=0.0, nu=64, nv=80, x0=0.0, z0=0.0):
+    """open-ended tube along y (like a vessel segment): centre line x = x0 + bend*sin(pi*y/length)"""
+    ys = np.linspace(0.0, length, nv + 1)
+    ph = np.linspace(0.0, 2 * np.pi, nu + 1)[:-1]
+    P = np.array([[[x0 + bend * np.sin(np.pi * y / length) + r * np.cos(p), y, z0 + r * np.sin(p)] for p in ph] for y in ys])
+    tris = []
+    for i in range(nv):
+        for j in range(nu):
+            a, b, c, d = P[i, j], P[i, (j + 1) % nu], P[i + 1, (j + 1) % nu], P[i + 1, j]
+            tris += [[a, b, c], [a, c, d]]
+    return np.array(tris, dtype=np.float32)
+
+
+def write_binary_stl(path, tri):
+    tri = np.asarray(tri, dtype=np.float32).reshape(-1, 3, 3)
+    rec = np.zeros(len(tri), dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    rec["v"] = tri
+    with open(path, "wb") as f:
+        f.write(b"binary stl written by the tests".ljust(80, b" "))
+        f.write(np.uint32(len(tri)).tobytes())
+        f.write(rec.tobytes())
+
+
+def write_ascii_stl(path, tri):
+    tri = np.asarray(tri, dtype=np.float32).reshape(-1, 3, 3)
+    with open(path, "w") as f:
+        f.write("solid t\n")
+        for t in tri:
+            f.write(" facet normal 0 0 0\n  outer loop\n")
+            for v in t:
+                f.write(f"   vertex {float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")
+            f.write("  endloop\n endfacet\n")
+        f.write("endsolid t\n")
