@@ -1,6 +1,6 @@
 """Pin of the voxeliser against the reference's own data: bifurcation/bif.stl voxelised on the
-64 x 83 x 32 grid of bifurcation/geo.txt, grid origin and spacing fitted for the best overlap (the
-MATLAB step that made geo.txt is not shipped).  Writes tests/golden/bif_voxel_fit.json.
+64 x 83 x 32 grid of bifurcation/geo.txt at the reference's own spacing CH (bifurcation.cu:20), grid
+origin fitted for the best overlap (the MATLAB step that made geo.txt is not shipped).  Writes tests/golden/bif_voxel_fit.json.
 
   python tools/voxelise_bif.py            # CPU oracle (this container: needs /root/reference)
 """
@@ -26,22 +26,21 @@ def main():
         m = O.voxelize(tri, lo + np.asarray(off) * h, h, (64, 83, 32))
         return int((m & geo).sum()) / int((m | geo).sum()), m
 
+    H_REF = 0.248925  # the reference's lattice spacing in mm: CH = 0.000248925f m (bifurcation.cu:20)
     best = (0.0, None)
-    for h in (0.245, 0.2475, 0.25, 0.2525):  # coarse
-        for dx in np.arange(-2.5, -1.49, 0.25):
-            for dz in np.arange(-2.0, -0.99, 0.25):
-                for dy in np.arange(-2.5, -0.49, 0.5):
-                    s, _ = score(h, (dx, dy, dz))
-                    if s > best[0]:
-                        best = (s, (h, dx, dy, dz))
-    h0, dx0, dy0, dz0 = best[1]
-    for h in (h0 - 0.00125, h0, h0 + 0.00125):  # fine
-        for dx in dx0 + np.arange(-0.1875, 0.19, 0.0625):
-            for dz in dz0 + np.arange(-0.1875, 0.19, 0.0625):
-                for dy in dy0 + np.arange(-0.25, 0.26, 0.125):
-                    s, _ = score(h, (dx, dy, dz))
-                    if s > best[0]:
-                        best = (s, (h, dx, dy, dz))
+    for dx in np.arange(-2.5, -1.49, 0.25):  # coarse: where the grid sits relative to the surface's bounding box
+        for dz in np.arange(-2.0, -0.99, 0.25):
+            for dy in np.arange(-2.5, -0.49, 0.5):
+                s, _ = score(H_REF, (dx, dy, dz))
+                if s > best[0]:
+                    best = (s, (H_REF, dx, dy, dz))
+    _, dx0, dy0, dz0 = best[1]
+    for dx in dx0 + np.arange(-0.1875, 0.19, 0.0625):  # fine
+        for dz in dz0 + np.arange(-0.1875, 0.19, 0.0625):
+            for dy in dy0 + np.arange(-0.25, 0.26, 0.125):
+                s, _ = score(H_REF, (dx, dy, dz))
+                if s > best[0]:
+                    best = (s, (H_REF, dx, dy, dz))
     h, dx, dy, dz = best[1]
     s, m = score(h, (dx, dy, dz))
     diff = m != geo
