@@ -23,7 +23,7 @@ constexpr int SPARSE_BLOCK = 128;
 #define LBM_SP64_MINB 5
 #endif
 #ifndef LBM_SP32_MINB
-#define LBM_SP32_MINB 8
+#define LBM_SP32_MINB 10
 #endif
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID>
