@@ -574,7 +574,7 @@ struct Solver final : SolverBase {
         p.case_rule = d.case_rule;
         p.u_init = (T)d.u_max;
         // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
-        const char *force = getenv("LBM_SPECULATIVE");
+        static const char *const force = getenv("LBM_SPECULATIVE");  // tuning knob, read once
         p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
         return p;
     }
