@@ -82,6 +82,7 @@ struct StepParams {
     // for cell c, store_base[q][c] the slot its post-collision value goes to (storage mode folded in)
     const T *pull_base[Q];
     T *store_base[Q];
+    T *slot_base[Q];                // slot_base[q][c]: where cell c leaves the boundary value of its link q
     int case_rule;                  // lbm_case_rule (initial-state rule, for static links in the AA odd step)
     T u_init;                       // lbm_case_desc.u_max
 };

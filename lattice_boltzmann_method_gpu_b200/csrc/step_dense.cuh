@@ -230,7 +230,7 @@ __host__ __device__ __forceinline__ long long store_index(int q, long long c, lo
     return (long long)q * qs + c + off;
 }
 template <int MODE>
-__device__ __forceinline__ long long slot_index(int q, long long c, long long qs, long long off) {
+__host__ __device__ __forceinline__ long long slot_index(int q, long long c, long long qs, long long off) {
     if (MODE == MODE_AB) return (long long)q * qs + c - off;
     if (MODE == MODE_AA_EVEN) return (long long)oppq(q) * qs + c - off;
     return (long long)q * qs + c;
@@ -286,16 +286,13 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
         p.rho[c] = rho, p.ux[c] = ux, p.uy[c] = uy, p.uz[c] = uz;
     }
     if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));  // |u| as ldc.cu:464 forms it
-    if (p.peer_up || p.peer_dn) push_to_peers<T, MODE>(p, c - p.face_c0, node, f);
+    if (p.peer_up || p.peer_dn) push_to_peers<T, MODE>(p, (long long)c - p.face_c0, node, f);
     if (node & NODE_LINKS) {
         // wall links: half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
         const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (WALL_READY ? wallw : p.wall[c]);
 #pragma unroll
         for (int q = 1; q < Q; q++) {
-            if (wl & (1u << q)) {
-                const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                dst[slot_index<MODE>(q, c, p.qstride, off)] = f[oppq(q)];
-            }
+            if (wl & (1u << q)) p.slot_base[q][c] = f[oppq(q)];
         }
         // what is left is an inlet/outlet/lid link (slow path) or a static link, whose slot is never
         // rewritten -- except by the odd in-place step, which has to restore it
@@ -304,13 +301,10 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
             T gl[Q], hv[Q];  // copies in local memory on this path only: f[] itself stays in registers
 #pragma unroll
             for (int q = 0; q < Q; q++) gl[q] = f[q];
-            const uint32_t wm = boundary_node<T>(p, c, rest, MODE, rho, ux, uy, uz, gl, hv);
+            const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, hv);
 #pragma unroll
             for (int q = 1; q < Q; q++) {
-                if (wm & (1u << q)) {
-                    const long long off = (long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q);
-                    dst[slot_index<MODE>(q, c, p.qstride, off)] = hv[q];
-                }
+                if (wm & (1u << q)) p.slot_base[q][c] = hv[q];
             }
         }
     }
@@ -319,6 +313,9 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool SPEC, int CFG, int MODE>
 __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(const __grid_constant__ StepParams<T> p) {
     const Box &b = p.box;
+    // 64-bit cell ids on purpose: 32-bit ones turn every address into one IMAD.WIDE.U32 instead of an
+    // IADD3 pair (-22 instructions per thread), which changes nothing in fp64 and costs 6 % in fp32,
+    // where IMAD shares its pipe with the collision's FFMAs (profiles/r01_notes.md)
     const long long c = p.c_begin + (long long)blockIdx.x * cfg_block(CFG) + threadIdx.x;
     if (c >= p.c_end) return;  // ranges are whole planes (multiples of 32 cells): warp-uniform
     T f[Q];
@@ -377,6 +374,7 @@ void set_bases(StepParams<T> &p) {
         const long long off = (long long)cxq(q) + (long long)p.box.px * cyq(q) + p.box.plane * czq(q);
         p.pull_base[q] = p.src + pull_index<MODE>(q, 0, p.qstride, off);
         p.store_base[q] = p.dst + store_index<MODE>(q, 0, p.qstride, off);
+        p.slot_base[q] = p.dst + slot_index<MODE>(q, 0, p.qstride, off);
     }
 }
 
