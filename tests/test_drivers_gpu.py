@@ -37,6 +37,12 @@ def test_bifurcation_driver_matches_reference_files(tmp_path):
     assert lines[:9] == [str(s) for s in GOLD["bif_header"]]
     body = np.array(lines[9].split(), dtype=np.float32).reshape(30, 79, 62, 3)
     compare("bif", body, 2e-5)
+    # write_once (bif:1055-1075): u_y, then u_x, of the whole plane z = NZ/2 in lattice units
+    meas = np.array((tmp_path / "meas1.txt").read_text().split(), dtype=np.float64).reshape(2, 83, 64)
+    c_u = 0.24159041  # bif:20
+    assert np.allclose(meas[0][2:81, 1:63] * c_u, body[16 - 1, :, :, 1], rtol=2e-5, atol=1e-9)
+    assert np.allclose(meas[1][2:81, 1:63] * c_u, body[16 - 1, :, :, 0], rtol=2e-5, atol=1e-9)
+    assert np.abs(meas[0]).max() > 0.05
 
 
 def test_driver_reports_missing_geometry(tmp_path):
