@@ -1,4 +1,4 @@
-/* CPU restatement of the STL voxeliser (TEST INFRASTRUCTURE ONLY -- used by tests/ and tools/, never
+/* CPU restatement of the STL voxeliser (TEST INFRASTRUCTURE ONLY -- used by tests/, never
  * by the product library; the product is csrc/lbm_voxel.cu).
  *
  * The reference ships the carotid surface (bifurcation/bif.stl) and its voxelisation
@@ -6,7 +6,7 @@
  * (bifurcation/README.md:1-5); this is the published ray-parity algorithm
  * (solid voxelisation, Schwarz & Seidel 2010, with the rasteriser's top-left tie rule), pinned by
  * reproducing the shipped geo.txt from the shipped bif.stl up to surface voxels
- * (tools/voxelise_bif.py, tests/test_voxel_cpu.py).  "parity partial": the original tool is absent.
+ * (tests/golden/make_voxel_fit.py, tests/test_voxel_cpu.py).  "parity partial": the original tool is absent.
  *
  * Voxel (i,j,k) has its centre at origin + (i+.5, j+.5, k+.5) * h.  A ray along +x through the centre
  * of every (j,k) row is intersected with every triangle; a crossing at abscissa xc toggles the marker

@@ -2,7 +2,7 @@
 64 x 83 x 32 grid of bifurcation/geo.txt at the reference's own spacing CH (bifurcation.cu:20), grid
 origin fitted for the best overlap (the MATLAB step that made geo.txt is not shipped).  Writes tests/golden/bif_voxel_fit.json.
 
-  python tools/voxelise_bif.py            # CPU oracle (this container: needs /root/reference)
+  python tests/golden/make_voxel_fit.py            # CPU oracle (this container: needs /root/reference)
 """
 import json
 import sys
@@ -10,7 +10,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import oracle as O  # noqa: E402
 

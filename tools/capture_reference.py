@@ -7,7 +7,10 @@ oracle and the CUDA path can be pinned to the REAL reference.
 Per case it stores <case>.npz with the final velocity field parsed from the last VTK the
 program wrote (float32, VTK order), the iteration number in that file's name, the lines of
 out/CONVERGENCE.log and the program's stdout.  tests/golden/make_reference_golden.py turns
-these captures into the small committed fixtures."""
+these captures into the small committed fixtures.
+MEASUREMENT / TEST INFRASTRUCTURE (like tests/): it may run the compiled reference in oracle/_ref or use the
+test helpers; nothing here is part of, or imported by, the product package.
+"""
 import re
 import shutil
 import subprocess

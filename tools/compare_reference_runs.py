@@ -4,6 +4,9 @@ shipped configurations, each timed by its own "TOTAL RUNNING TIME" line (the ref
 span around its main loop, VTK dumps and per-step residual included; ours: the same loop).
 
   python tools/compare_reference_runs.py > profiles/r01_reference_vs_ours_64.txt
+
+MEASUREMENT / TEST INFRASTRUCTURE (like tests/): it may run the compiled reference in oracle/_ref or use the
+test helpers; nothing here is part of, or imported by, the product package.
 """
 import re
 import shutil

@@ -2,6 +2,9 @@
 must equal the single-domain run computed on rank 0, bit for bit.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/mgpu_check.py
+
+MEASUREMENT / TEST INFRASTRUCTURE (like tests/): it may run the compiled reference in oracle/_ref or use the
+test helpers; nothing here is part of, or imported by, the product package.
 """
 import os
 import sys

@@ -1,4 +1,7 @@
-"""20 steps of the 64^3 cavity and the bifurcation (for an ncu launch list: how long is the step kernel itself)."""
+"""20 steps of the 64^3 cavity and the bifurcation (for an ncu launch list: how long is the step kernel itself).
+MEASUREMENT / TEST INFRASTRUCTURE (like tests/): it may run the compiled reference in oracle/_ref or use the
+test helpers; nothing here is part of, or imported by, the product package.
+"""
 import sys
 from pathlib import Path
 
