@@ -8,7 +8,8 @@
 //                voxel centres; a crossing toggles the marker bit of the first voxel beyond it
 //                (atomicXor -- order-independent, so the result is deterministic)
 //   k_vox_fill : one warp per row: prefix XOR of the marker bits (in-word shifts + a warp scan of the
-//                word parities) -> one byte per voxel, coalesced
+//                word parities) -> one byte per voxel, coalesced; rows with an odd number of crossings
+//                (leaks at the ragged rim of an open end) are cleared
 // A z-range can be voxelised on its own (what one rank of a z-slab run hands to lbm_set_flag_slab).
 #include <cuda_runtime.h>
 
@@ -109,6 +110,10 @@ __global__ void k_vox_fill(const uint32_t *mark, Grid g, long long nrows, int W,
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= nrows) return;
+    // a row with an odd number of crossings (ray through the ragged rim of an open end) is cleared
+    unsigned total = 0;
+    for (int w = lane; w < W; w += 32) total ^= (unsigned)__popc(mark[(size_t)row * W + w]) & 1u;
+    total = __reduce_xor_sync(0xffffffffu, total);
     unsigned carry = 0;  // parity of all marker bits of the words before this group
     for (int w0 = 0; w0 < W; w0 += 32) {
         const int w = w0 + lane;
@@ -124,6 +129,7 @@ __global__ void k_vox_fill(const uint32_t *mark, Grid g, long long nrows, int W,
         }
         const unsigned before = (incl ^ p) ^ carry;
         if (before) m = ~m;
+        if (total) m = 0u;
         carry ^= __shfl_sync(0xffffffffu, incl, 31);
         if (w < W) {
             uint8_t *o = out + (size_t)row * g.nx + (size_t)w * 32;

@@ -15,6 +15,9 @@
  * y are fine).  Ties (centre exactly on a projected edge or vertex) are broken so that two triangles
  * sharing an edge claim its points exactly once when they lie on opposite sides of it in the
  * projection, and zero or two times when they lie on the same side (a silhouette edge).
+ * A row with an ODD number of crossings (its ray passes the ragged rim of an open end and meets only one
+ * of the two walls) has no inside/outside answer; it is cleared, so a leak never paints the row to the
+ * edge of the box.
  *
  * All arithmetic in double, no FMA contraction (-ffp-contract=off): the CUDA kernel, compiled with
  * -fmad=false, produces the same bits.
@@ -105,10 +108,11 @@ int vox_oracle(const float *tri, int64_t ntri, const vox_grid *g, int32_t z_begi
         for (int j = 0; j < ny; j++) {
             const uint32_t *m = mark + ((size_t)k * ny + j) * W;
             uint8_t *o = out + ((size_t)k * ny + j) * nx;
-            unsigned par = 0;
+            unsigned par = 0, total = 0;
+            for (int w = 0; w < W; w++) total ^= (unsigned)__builtin_popcount(m[w]) & 1u;
             for (int i = 0; i < nx; i++) {
                 par ^= (m[i >> 5] >> (i & 31)) & 1u;
-                o[i] = (uint8_t)par;
+                o[i] = (uint8_t)(total ? 0u : par);
             }
         }
     free(mark);

@@ -68,6 +68,18 @@ def test_open_tube_slabs_and_triangle_order():
     assert abs(area / (np.pi * 9.0) - 1) < 0.03
 
 
+def test_rows_through_a_ragged_rim_are_cleared():
+    """triangles missing at an open end: rays that meet only one wall there have no inside/outside
+    answer; such rows come out empty instead of painted to the edge of the box"""
+    tri = H.mesh_tube(20.0, 3.0, x0=6.0, z0=5.0)
+    ragged = np.delete(tri, np.arange(len(tri) - 40, len(tri) - 10), axis=0)  # a hole in the last ring, one side only
+    grid = ((0.0, 0.0, 0.0), 0.25, (48, 80, 40))
+    full, m = O.voxelize(tri, *grid), O.voxelize(ragged, *grid)
+    assert m[:, :, -1].sum() == 0 and m[:, :, 0].sum() == 0   # nothing leaks to the box edge
+    assert np.array_equal(m[:, :78], full[:, :78])             # rows away from the hole are untouched
+    assert 0 < m[:, 78:].sum() < full[:, 78:].sum()            # rows through the hole are cleared
+
+
 @pytest.mark.skipif(not REF.exists(), reason="reference tree not present (GPU box)")
 def test_shipped_bif_stl_reproduces_shipped_geo_txt():
     """the one pin the reference offers for this row: its own surface and its own voxelisation"""
@@ -79,4 +91,5 @@ def test_shipped_bif_stl_reproduces_shipped_geo_txt():
     assert inter / union == pytest.approx(fit["iou"], abs=1e-12)
     assert inter / union > 0.96
     assert int(m.sum()) == fit["inside_voxels"]
+    assert m[:, :, -1].sum() == 0 and m[:, :, 0].sum() == 0  # the ragged outlet rim does not leak
     assert int(np.packbits(m).astype(np.uint64).sum()) == fit["packed_checksum"]

@@ -19,6 +19,7 @@ MESHES = {
     "box": lambda: H.mesh_box((1.0, 1.0, 1.0), (5.0, 5.0, 5.0)),
     "sphere": lambda: H.mesh_sphere((8.1, 7.9, 8.3), 6.0, nu=96, nv=48),
     "tube": lambda: H.mesh_tube(20.0, 3.0, bend=1.5, x0=6.0, z0=5.0),
+    "ragged": lambda: np.delete(H.mesh_tube(20.0, 3.0, x0=6.0, z0=5.0), np.arange(10240 - 40, 10240 - 10), axis=0),
 }
 
 
@@ -28,6 +29,7 @@ MESHES = {
     ("sphere", (0.0, 0.0, 0.0), 0.31, (53, 53, 53)),
     ("sphere", (-3.0, 2.0, 5.0), 0.173, (120, 40, 33)),   # surface leaves the grid on several sides
     ("tube", (0.0, 0.0, 0.0), 0.25, (48, 80, 40)),
+    ("ragged", (0.0, 0.0, 0.0), 0.25, (48, 80, 40)),      # rows with an odd number of crossings are cleared
     ("tube", (0.0, 0.0, 0.0), 0.01, (1100, 6, 5)),        # rows longer than 1024 voxels (several word groups)
 ])
 def test_gpu_equals_oracle(mesh, origin, h, dims):
