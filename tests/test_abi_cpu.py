@@ -68,3 +68,36 @@ def test_bad_descriptor_is_rejected():
     h = C.c_void_p()
     assert lib.lbm_create(C.byref(d), C.byref(h)) == -1
     assert b"size mismatch" in lib.lbm_last_error(None)
+
+
+def test_voxeliser_argument_errors_need_no_gpu(tmp_path):
+    """the front end checks its arguments and reads the surface file before it touches the device, and
+    -- like the solver -- has no CPU fallback for the voxelisation itself"""
+    import numpy as np
+    import torch
+
+    grid = ((0.0, 0.0, 0.0), 0.5, (8, 8, 8))
+    with pytest.raises(L.LbmError) as e:
+        L.voxelize(tmp_path / "missing.stl", *grid)
+    assert "missing.stl" in str(e.value)
+    (tmp_path / "junk.stl").write_bytes(b"solid nothing\nendsolid\n")
+    with pytest.raises(L.LbmError):
+        L.voxelize(tmp_path / "junk.stl", *grid)
+    tri = np.zeros((1, 3, 3), np.float32)
+    for bad in (dict(spacing=0.0), dict(dims=(0, 8, 8)), dict(z_range=(4, 9)), dict(z_range=(5, 5))):
+        args = dict(origin=(0.0, 0.0, 0.0), spacing=0.5, dims=(8, 8, 8))
+        args.update(bad)
+        with pytest.raises(L.LbmError) as e:
+            L.voxelize(tri, **args)
+        assert e.value.status == -1  # LBM_ERR_ARG
+    if not torch.cuda.is_available():
+        with pytest.raises(L.LbmError) as e:
+            L.voxelize(tri, *grid)
+        assert e.value.status in (-4, -6)  # LBM_ERR_CUDA / LBM_ERR_NO_DEVICE: no silent CPU path
+
+
+def test_handle_calls_reject_null():
+    lib = L.load_library()
+    assert lib.lbm_set_output_format(None, 0) != 0
+    assert lib.lbm_output_save(None, 0) != 0
+    assert lib.lbm_step(None, 1) != 0
