@@ -14,7 +14,6 @@ visible, construction raises.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import os
 from pathlib import Path
 

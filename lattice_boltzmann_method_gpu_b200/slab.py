@@ -13,7 +13,6 @@ Nothing here computes: the kernels live in liblbm_b200.so.  `exchange_halos` and
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 
