@@ -384,6 +384,15 @@ def main():
                     help="dram__bytes_read.sum+dram__bytes_write.sum per launch from the committed ncu capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started by hand without a launcher: become `torchrun --nproc-per-node N bench.py ...` (one rank per GPU)
+        import socket
+
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         run_reference_arm(args)
     else:
