@@ -1,5 +1,5 @@
 #!/bin/bash
-# occupancy variants of the step kernel (variants/liblbm_<f64 CTAs per SM>_<f32 CTAs per SM>.so, built with -DLBM_F64_MINB / -DLBM_F32_MINB)
+# occupancy variants of the step kernel: build them first with tools/build_variants.sh "6 10" "7 12" (variants/liblbm_<f64 CTAs per SM>_<f32 CTAs per SM>.so)
 cd /root/repo
 LIB=lattice_boltzmann_method_gpu_b200/liblbm_b200.so
 cp $LIB /tmp/lib_default.so
