@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "lbm_internal.h"
+#include "vtk_format.h"
 
 namespace lbm {
 
@@ -161,11 +162,39 @@ struct Solver final : SolverBase {
     // the LDC rule stores every node of the box (ldc.cu:54); the others store geo != 0
     int store_all() const { return d.case_rule == LBM_CASE_LDC ? 1 : 0; }
 
+    std::vector<std::pair<void *, size_t>> allocs;  // what dalloc handed out (for dev_bytes and dfree)
     template <typename U>
     int dalloc(U **p, size_t n) {
         CK(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(U)));
         dev_bytes += (int64_t)(n * sizeof(U));
+        allocs.emplace_back((void *)*p, n * sizeof(U));
         return 0;
+    }
+    template <typename U>
+    void dfree(U **p) {
+        if (!*p) return;
+        for (auto &a : allocs)
+            if (a.first == (void *)*p) {
+                dev_bytes -= (int64_t)a.second;
+                a = allocs.back();
+                allocs.pop_back();
+                break;
+            }
+        cudaFree((void *)*p);
+        *p = nullptr;
+    }
+    // Buffers whose size depends on the GEOMETRY (stored-node counts, records, face sizes) and not only
+    // on the box: released whenever geo_pre runs again, so that a handle re-initialised with a larger
+    // mask never writes past allocations sized for the previous one.
+    void release_geometry_sized() {
+        if (d_fb == d_fa) d_fb = nullptr;
+        dfree(&d_fa), dfree(&d_fb), dfree(&d_rho), dfree(&d_ux), dfree(&d_uy), dfree(&d_uz);
+        for (int sd = 0; sd < 2; sd++) dfree(&d_send[sd]), dfree(&d_recv[sd]);
+        dfree(&d_cart), dfree(&d_nodec), dfree(&d_wallc), dfree(&d_labelc), dfree(&d_rec), dfree(&d_chunk_cnt);
+        dfree(&d_chunk_off), dfree(&d_plane_seg);
+        if (d_stage) cudaFree(d_stage), d_stage = nullptr, stage_elems = 0;
+        d_cur = d_nxt = nullptr;
+        for (int sd = 0; sd < 2; sd++) peer_buf[sd][0] = peer_buf[sd][1] = nullptr;
     }
 
     int setup() {
@@ -294,7 +323,9 @@ struct Solver final : SolverBase {
         CK(cudaMemcpyAsync(&c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         stored_own = c;
-        have_geo = true, have_index = false, have_init = false;
+        if (have_init && sparse) release_geometry_sized();
+        have_geo = true, have_index = false, have_init = false, have_moments = false;
+        w_index.clear(), w_rho.clear(), w_ux.clear(), w_uy.clear(), w_uz.clear();  // host mirrors of the old tables
         return 0;
     }
 
@@ -305,6 +336,8 @@ struct Solver final : SolverBase {
     }
     int set_compact_offset(int64_t off, int64_t total) override {
         compact_first = off, compact_total = total, offset_set = true;
+        have_index = false, have_init = false;  // the index table is numbered from `off`
+        w_index.clear();
         return 0;
     }
 
@@ -350,7 +383,8 @@ struct Solver final : SolverBase {
         nfluid = nf;
         n_lo_stored = n_lo, stored_box = nbox, sp_first = (long long)compact_first - n_lo;
         plane_first[(size_t)(box.z1 - box.z0)] = sp_first + nbox;
-        have_index = true;
+        have_index = true, have_init = false;
+        w_index.clear();
         if (nlat) *nlat = compact_total;
         return 0;
     }
@@ -512,7 +546,7 @@ struct Solver final : SolverBase {
         CK(cudaMemcpyAsync(&nseg, d_cnt + 5, sizeof nseg, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         if (own_id1 <= own_id0) nseg = 0;
-        if (d_rec) cudaFree(d_rec), d_rec = nullptr;
+        dfree(&d_rec);
         if (dalloc(&d_rec, (size_t)std::max<long long>(nseg, 1) * SEG_REC)) return LBM_ERR_NOMEM;
         CK(cudaMemsetAsync(d_rec, 0, (size_t)std::max<long long>(nseg, 1) * SEG_REC * sizeof(int32_t), st));
         CK(cudaMemsetAsync(d_plane_seg, 0x7f, ((size_t)nown + 1) * sizeof(long long), st));  // "no record yet"
@@ -718,7 +752,37 @@ struct Solver final : SolverBase {
         char magic[8];
         int32_t version, case_rule, nx, ny, nz, z_begin, z_end, precision, storage, reserved;
         int64_t steps, qstride, elems;
+        uint64_t case_hash;  // labels of the state box, tau, BC table, pulse parameters
     };
+    // FNV-1a over the parameters a continued run depends on, seeded with an order-independent
+    // device-side hash of the label field
+    int case_hash(uint64_t *out) {
+        CK(cudaMemsetAsync(d_cnt + 6, 0, sizeof(long long), st));
+        CK(launch_label_hash(d_label, box.cells(), (unsigned long long *)(d_cnt + 6), st));
+        launches++;
+        unsigned long long hv = 0;
+        CK(cudaMemcpyAsync(&hv, d_cnt + 6, sizeof hv, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t h = 1469598103934665603ull ^ hv;
+        auto mix = [&h](const void *p, size_t n) {
+            const unsigned char *b = (const unsigned char *)p;
+            for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+        };
+        mix(&d.tau, sizeof d.tau), mix(&d.u_max, sizeof d.u_max);
+        mix(&d.pulse_amp, sizeof d.pulse_amp), mix(&d.pulse_period, sizeof d.pulse_period);
+        for (int i = 0; i < LBM_MAX_BC; i++) {
+            const BcEntry &e = bc[i];
+            const int v[6] = {e.kind, e.naxis, e.nsign, e.vaxis, e.source, e.pulsatile};
+            mix(v, sizeof v), mix(&e.value, sizeof e.value), mix(&e.init_value, sizeof e.init_value);
+        }
+        mix(&nfluid, sizeof nfluid), mix(&stored_box, sizeof stored_box);
+        if (have_planes) mix(h_in.data(), h_in.size() * sizeof(float)), mix(h_out.data(), h_out.size() * sizeof(float));
+        *out = h;
+        return 0;
+    }
+    // The population buffer travels through a bounded pinned staging buffer (two halves, the copy of one
+    // overlapping the file I/O of the other): at 512^3 fp64 the buffer is 20 GB, which must not be mirrored
+    // in pageable host memory.
     int checkpoint(const char *path, bool save) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "checkpoint before initialize");
         if (in_step) FAIL(LBM_ERR_STATE, "checkpoint inside lbm_step_begin / lbm_step_end");
@@ -730,40 +794,78 @@ struct Solver final : SolverBase {
         const size_t elems = (size_t)qstride * Q;
         CkptHeader hd{};
         memcpy(hd.magic, "LBMB200", 8);
-        hd.version = 1, hd.case_rule = d.case_rule, hd.nx = d.nx, hd.ny = d.ny, hd.nz = d.nz;
+        hd.version = 2, hd.case_rule = d.case_rule, hd.nx = d.nx, hd.ny = d.ny, hd.nz = d.nz;
         hd.z_begin = d.z_begin, hd.z_end = d.z_end, hd.precision = d.precision, hd.storage = d.storage;
         hd.steps = steps, hd.qstride = qstride, hd.elems = (int64_t)elems;
-        std::vector<T> host(elems);
+        int r = case_hash(&hd.case_hash);
+        if (r) return r;
+        const size_t half = (size_t)(32u << 20) / sizeof(T);  // elements per staging half (32 MiB)
+        T *stage = nullptr;
+        CK(cudaMallocHost((void **)&stage, 2 * half * sizeof(T)));
+        cudaEvent_t evh[2] = {nullptr, nullptr};
+        FILE *f = nullptr;
+        int rc = 0;
+        auto done = [&](int code, const std::string &msg) {
+            if (f) fclose(f);
+            for (auto &e : evh)
+                if (e) cudaEventDestroy(e);
+            cudaFreeHost(stage);
+            if (code) err = msg;
+            return code;
+        };
+        for (auto &e : evh)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return done(LBM_ERR_CUDA, "cudaEventCreate failed");
+        const size_t nchunk = (elems + half - 1) / half;
+        auto chunk_len = [&](size_t k) { return std::min(half, elems - k * half); };
         if (save) {
-            FILE *f = fopen(path, "wb");
-            if (!f) FAIL(LBM_ERR_IO, "cannot write '%s'", path);
-            CK(cudaMemcpy(host.data(), d_cur, elems * sizeof(T), cudaMemcpyDeviceToHost));
-            bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && fwrite(host.data(), sizeof(T), elems, f) == elems;
-            fclose(f);
-            if (!ok) FAIL(LBM_ERR_IO, "short write to '%s'", path);
-            return 0;
+            f = fopen(path, "wb");
+            if (!f) return done(LBM_ERR_IO, fmt("cannot write '%s'", path));
+            if (fwrite(&hd, sizeof hd, 1, f) != 1) return done(LBM_ERR_IO, fmt("short write to '%s'", path));
+            for (size_t k = 0; k <= nchunk; k++) {
+                if (k < nchunk) {  // start the copy of chunk k ...
+                    if (cudaMemcpyAsync(stage + (k & 1) * half, d_cur + k * half, chunk_len(k) * sizeof(T), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                        cudaEventRecord(evh[k & 1], st) != cudaSuccess)
+                        return done(LBM_ERR_CUDA, "checkpoint: device-to-host copy failed");
+                }
+                if (k > 0) {  // ... while chunk k-1 goes to the file
+                    if (cudaEventSynchronize(evh[(k - 1) & 1]) != cudaSuccess) return done(LBM_ERR_CUDA, "checkpoint: copy failed");
+                    const size_t n = chunk_len(k - 1);
+                    if (fwrite(stage + ((k - 1) & 1) * half, sizeof(T), n, f) != n) return done(LBM_ERR_IO, fmt("short write to '%s'", path));
+                }
+            }
+            rc = fclose(f), f = nullptr;
+            return done(rc ? LBM_ERR_IO : 0, fmt("short write to '%s'", path));
         }
-        FILE *f = fopen(path, "rb");
-        if (!f) FAIL(LBM_ERR_IO, "cannot open '%s'", path);
+        f = fopen(path, "rb");
+        if (!f) return done(LBM_ERR_IO, fmt("cannot open '%s'", path));
         CkptHeader in{};
-        bool ok = fread(&in, sizeof in, 1, f) == 1;
-        if (ok && (memcmp(in.magic, hd.magic, 8) || in.version != 1 || in.case_rule != hd.case_rule || in.nx != hd.nx ||
-                   in.ny != hd.ny || in.nz != hd.nz || in.z_begin != hd.z_begin || in.z_end != hd.z_end ||
-                   in.precision != hd.precision || in.storage != hd.storage || in.qstride != hd.qstride ||
-                   in.elems != hd.elems)) {
-            fclose(f);
-            FAIL(LBM_ERR_ARG, "checkpoint '%s' was written for a different case / slab / precision / storage", path);
-        }
-        ok = ok && fread(host.data(), sizeof(T), elems, f) == elems;
-        fclose(f);
-        if (!ok) FAIL(LBM_ERR_IO, "short read from '%s'", path);
-        steps = in.steps;
+        if (fread(&in, sizeof in, 1, f) != 1) return done(LBM_ERR_IO, fmt("short read from '%s'", path));
+        if (memcmp(in.magic, hd.magic, 8) || in.version != hd.version || in.case_rule != hd.case_rule || in.nx != hd.nx ||
+            in.ny != hd.ny || in.nz != hd.nz || in.z_begin != hd.z_begin || in.z_end != hd.z_end ||
+            in.precision != hd.precision || in.storage != hd.storage || in.qstride != hd.qstride || in.elems != hd.elems)
+            return done(LBM_ERR_ARG, fmt("checkpoint '%s' was written for a different case / slab / precision / storage", path));
+        if (in.case_hash != hd.case_hash)
+            return done(LBM_ERR_ARG, fmt("checkpoint '%s' was written for a different geometry, tau or boundary table", path));
         // two-buffer storage alternates with the step parity; keep "current" consistent with it
-        d_cur = (d_fb != d_fa && (steps & 1)) ? d_fb : d_fa;
+        T *target = (d_fb != d_fa && (in.steps & 1)) ? d_fb : d_fa;
+        for (size_t k = 0; k < nchunk; k++) {
+            if (k >= 2 && cudaEventSynchronize(evh[k & 1]) != cudaSuccess) return done(LBM_ERR_CUDA, "checkpoint: copy failed");
+            const size_t n = chunk_len(k);
+            if (fread(stage + (k & 1) * half, sizeof(T), n, f) != n) {
+                cudaStreamSynchronize(st);
+                have_init = false;  // the state is partly overwritten
+                return done(LBM_ERR_IO, fmt("short read from '%s' (the handle must be re-initialised)", path));
+            }
+            if (cudaMemcpyAsync(target + k * half, stage + (k & 1) * half, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(evh[k & 1], st) != cudaSuccess)
+                return done(LBM_ERR_CUDA, "checkpoint: host-to-device copy failed");
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) return done(LBM_ERR_CUDA, "checkpoint: copy failed");
+        steps = in.steps;
+        d_cur = target;
         d_nxt = d_cur == d_fa ? d_fb : d_fa;
-        CK(cudaMemcpy(d_cur, host.data(), elems * sizeof(T), cudaMemcpyHostToDevice));
         have_moments = false;
-        return 0;
+        return done(0, "");
     }
 
     int p2p_export(lbm_ipc_handle *h2, void **ptrs, int64_t *boff, int64_t *qs, int64_t *halo_c0, int64_t *face_c0) override {
@@ -1057,12 +1159,7 @@ struct Solver final : SolverBase {
         // z-planes are formatted by several host threads into their own buffers and written in order.
         const int nzp = z1 - z0;
         const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, nzp}));
-        auto put = [](std::string &buf, auto v) {
-            char tmp[48];
-            auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::general, 6);
-            buf.append(tmp, r.ptr);
-            buf.push_back(' ');
-        };
+        auto put = [](std::string &buf, auto v) { vtk_put(buf, v); };
         // kind 0: density, 1: pressure, 2: velocity
         auto format_planes = [&](int kind, std::vector<std::string> &parts) {
             parts.assign((size_t)nthr, std::string());

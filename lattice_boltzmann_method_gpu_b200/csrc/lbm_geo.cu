@@ -686,6 +686,19 @@ cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells
     k_scatter_index<<<(unsigned)ntiles, SCAN_BLOCK, 0, s>>>(label, index, cells, sr, base, offsets, plane, plane_first_dev);
     return cudaGetLastError();
 }
+// sum over cells of (label + 2) * odd multiplier of the cell id: commutative, so the atomics may land in any order
+__global__ void k_label_hash(const int32_t *label, long long cells, unsigned long long *out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (c < cells) v = (unsigned long long)(label[c] + 2) * (((unsigned long long)c * 0x9E3779B97F4A7C15ull) | 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+cudaError_t launch_label_hash(const int32_t *label, long long cells, unsigned long long *out_dev, cudaStream_t s) {
+    k_label_hash<<<nblocks(cells, 256), 256, 0, s>>>(label, cells, out_dev);
+    return cudaGetLastError();
+}
 cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
                                 cudaStream_t s) {
     StoredRule sr{px, nx, all};

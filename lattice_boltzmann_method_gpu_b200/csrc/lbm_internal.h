@@ -112,6 +112,8 @@ cudaError_t launch_compact(const int32_t *label, int32_t *index, long long cells
                            long long base, int32_t *scratch, size_t scratch_ints, long long *total_out_dev,
                            long long plane, long long *plane_first_dev, cudaStream_t s);
 size_t compact_scratch_ints(long long cells);
+// order-independent 64-bit hash of a label field (checkpoint header)
+cudaError_t launch_label_hash(const int32_t *label, long long cells, unsigned long long *out_dev, cudaStream_t s);
 cudaError_t launch_count_stored(const int32_t *label, long long cells, int px, int nx, int all, long long *out_dev,
                                 cudaStream_t s);
 cudaError_t launch_node_words(const int32_t *label, uint32_t *node, uint32_t *wall, uint8_t *seg, int8_t *label8, Box box,

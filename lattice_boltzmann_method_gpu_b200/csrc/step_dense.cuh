@@ -32,7 +32,6 @@
 #include <cstdlib>
 #include "lattice.cuh"
 #include "lbm_internal.h"
-#include "init_rule.cuh"
 
 namespace lbm {
 
@@ -82,21 +81,21 @@ __device__ __forceinline__ T feq_bc_axis(T rw, int cs, T u) {
 //                              boundary slot of link q:        a[q][c]               (read by the even step)
 // AA-pattern streaming (Bailey et al. 2009) with the fluid-side boundaries of this file: every slot
 // a thread touches in a launch is touched by that thread only, so the update is in place.
-// The even step overwrites slot (q,c) of a link whose source is not fluid, therefore the ODD step
-// re-creates the constant of a static link there; in the other two modes static slots are simply
-// never written.
+// The even step overwrites slot (q,c) of a link whose source is not fluid, so in the two in-place
+// modes a static link CARRIES its constant along: the value pulled for it (the initial equilibrium of
+// its source, whatever that was) is written back, before the collision, into the slot the following
+// step pulls from.  Two-buffer storage never writes static slots.
 enum { MODE_AB = 0, MODE_AA_EVEN = 1, MODE_AA_ODD = 2 };
 
-// Slow path of a node next to an inlet / outlet / lid (or, in the odd in-place step, next to any
-// static source): the values this fluid node (cell c, moments rho/u, post-collision populations g)
-// must leave in the slots of its links `rest`; returns the mask of links to write (a static link
-// outside the odd AA step keeps its slot).  Out of line, so the bulk path stays small, and one call
+// Slow path of a node next to an inlet / outlet / lid: the values this fluid node (cell c, moments
+// rho/u, post-collision populations g, pulled populations fpre) must leave in the slots of its links
+// `rest`; returns the mask of links to write (a static link of the two-buffer storage keeps its slot).  Out of line, so the bulk path stays small, and one call
 // per NODE in three phases -- all source labels, then all prescribed speeds, then the arithmetic --
 // so that the dependent loads of the links overlap instead of queueing up link after link: these
 // few nodes set the lifetime of their CTA, which is what a small grid's step time consists of.
 template <typename T>
 __device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long c, uint32_t rest, int mode, T rho, T ux,
-                                               T uy, T uz, const T *g, T *out) {
+                                               T uy, T uz, const T *g, const T *fpre, T *out) {
     const Box &b = p.box;
     int x, y, zl;  // coordinates of the node, once (32-bit arithmetic when the cell id allows it)
     if (c < 0x7fffffffLL) {
@@ -148,12 +147,8 @@ __device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long
             }
             out[q] = tmp + (g[q] - feq) * p.om1;
             wm |= 1u << q;
-        } else if (mode == MODE_AA_ODD) {
-            // static link: the initial population of s, feq_q(1, u0(s))
-            T u0x, u0y, u0z;
-            init_velocity<T>(p.case_rule, p.u_init, p.bc, p.plane_in, p.plane_out, b, l, x - cxq(q), y - cyq(q),
-                             zl - czq(q) + b.z0, u0x, u0y, u0z);
-            out[q] = init_feq_q<T>(p.case_rule, q, T(1.0), u0x, u0y, u0z);
+        } else if (mode != MODE_AB) {
+            out[q] = fpre[q];  // static link, in-place storage: the constant travels with the link
             wm |= 1u << q;
         }
     }
@@ -267,10 +262,25 @@ __device__ __forceinline__ void push_to_peers(const StepParams<T> &p, long long 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, int MODE, bool WALL_READY>
 __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c, uint32_t node, uint32_t wallw, T (&f)[Q],
                                             double &velsum) {
-    const Box &b = p.box;
     T rho, ux, uy, uz;
+    // in-place storage: links that are neither walls nor (for nodes without NODE_HAS_BC) boundary links
+    // are static -- put the pulled constant back where the next step pulls it, before it is collided
+    T fpre[Q];
+    bool keep_pre = false;
+    if (MODE != MODE_AB && (node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) {
+        if (!WALL_READY) wallw = p.wall[c];
+        const uint32_t rest = node & NODE_LINKS & ~wallw;
+        if (rest && !(node & NODE_HAS_BC)) {
+#pragma unroll
+            for (int q = 1; q < Q; q++)
+                if (rest & (1u << q)) p.slot_base[q][c] = f[q];
+        } else if (rest) {
+            keep_pre = true;
+#pragma unroll
+            for (int q = 0; q < Q; q++) fpre[q] = f[q];
+        }
+    }
     collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-    T *dst = p.dst;
 #pragma unroll
     for (int q = 0; q < Q; q++) {
         if (MODE == MODE_AA_ODD) {
@@ -289,19 +299,23 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
     if (p.peer_up || p.peer_dn) push_to_peers<T, MODE>(p, (long long)c - p.face_c0, node, f);
     if (node & NODE_LINKS) {
         // wall links: half-way bounce-back, inline: the link's slot <- g_opp(q)(x)   (bif:781-798)
-        const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (WALL_READY ? wallw : p.wall[c]);
+        const uint32_t wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS)
+                                                     : ((WALL_READY || MODE != MODE_AB) ? (wallw & node & NODE_LINKS) : p.wall[c]);
 #pragma unroll
         for (int q = 1; q < Q; q++) {
             if (wl & (1u << q)) p.slot_base[q][c] = f[oppq(q)];
         }
-        // what is left is an inlet/outlet/lid link (slow path) or a static link, whose slot is never
-        // rewritten -- except by the odd in-place step, which has to restore it
+        // what is left is an inlet/outlet/lid link (slow path) or a static link (handled above)
         const uint32_t rest = node & NODE_LINKS & ~wl;
-        if (rest && ((node & NODE_HAS_BC) || MODE == MODE_AA_ODD)) {
+        if (rest && (node & NODE_HAS_BC)) {
             T gl[Q], hv[Q];  // copies in local memory on this path only: f[] itself stays in registers
 #pragma unroll
             for (int q = 0; q < Q; q++) gl[q] = f[q];
-            const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, hv);
+            if (!keep_pre) {  // two-buffer storage: never read
+#pragma unroll
+                for (int q = 0; q < Q; q++) fpre[q] = T(0.0);
+            }
+            const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, fpre, hv);
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 if (wm & (1u << q)) p.slot_base[q][c] = hv[q];

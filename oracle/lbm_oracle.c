@@ -18,7 +18,7 @@
  * Parity pin status: pinned by (a) the thesis' lattice count 65820 for the
  * shipped bifurcation geo.txt (tests/test_oracle_golden.py), (b) the analytic
  * Poiseuille profile, and (c) on a GPU box, outputs of the reference programs
- * themselves compiled unmodified into oracle/_ref (tests/test_reference_gpu.py).
+ * themselves compiled unmodified into oracle/_ref (tests/test_reference_outputs.py).
  * The pulsatile-inlet extension (pulse_amp != 0) has no reference code:
  * parity unpinned for that one feature.
  *
@@ -315,6 +315,11 @@ typedef struct {
     int nb;          /* boundary (label 1,2,3,5,6,7 / ldc 1,2) nodes */
     int32_t *blist;  /* their compact ids */
     REAL *bscratch;  /* 19*nb snapshot outputs */
+    /* ldc only: model of the order in which ldc.cu's `update` launch really executes (see
+     * orc_set_ldc_order): 0 = the defined semantics "all walls bounce, then fluid pulls" */
+    int ldc_order;
+    uint32_t *stale; /* [nfl] bit q: link q of this fluid node reads the wall slot BEFORE this launch's bounce */
+    int32_t *brow;   /* [nlat] row of a boundary node in bscratch, -1 otherwise */
 } FN(orc_state);
 
 #define CIDS(x, y, z) ((size_t)(x) + (size_t)s->nx * ((size_t)(y) + (size_t)s->ny * (size_t)(z)))
@@ -454,6 +459,7 @@ FN(orc_state) *FN(orc_create)(int case_id, int nx, int ny, int nz, const int32_t
     k = 0;
     for (int i = 0; i < nlat; i++)
         if (geo[s->cart[i]] == s->fluid_label) s->flist[k++] = i;
+#pragma omp parallel for schedule(static)
     for (int j = 0; j < s->nfl; j++) {
         size_t c = (size_t)s->cart[s->flist[j]];
         int x = (int)(c % nx), y = (int)((c / nx) % ny), z = (int)(c / ((size_t)nx * ny));
@@ -469,6 +475,7 @@ FN(orc_state) *FN(orc_create)(int case_id, int nx, int ny, int nz, const int32_t
 void FN(orc_destroy)(FN(orc_state) *s) {
     if (!s) return;
     free(s->geo), free(s->index), free(s->cart), free(s->blist), free(s->bscratch), free(s->flist), free(s->pull);
+    free(s->stale), free(s->brow);
     free(s->src), free(s->dst), free(s->rho), free(s->ux), free(s->uy), free(s->uz);
     free(s->inlety), free(s->outlety);
     free(s);
@@ -486,6 +493,52 @@ void FN(orc_set_cor_speeds)(FN(orc_state) *s, double uin, double uout, double us
     s->cor_uin = (REAL)uin, s->cor_uout = (REAL)uout, s->cor_usub = (REAL)usub;
 }
 void FN(orc_set_u_bc)(FN(orc_state) *s, double u_bc) { s->u_bc = (REAL)u_bc; }
+
+/* ldc only.  ldc.cu's `update` bounces the wall nodes IN PLACE on d_scr (ldc:75-202) in the same
+ * launch in which fluid nodes pull from them (ldc:204-313): whether a fluid node sees this launch's
+ * bounce ("fresh") or the slot's previous content -- the bounce of two iterations ago, the buffers
+ * alternate (ldc:664-666) -- ("stale") depends on the order the launch executes in.  Most of that
+ * order is fixed by the code: a thread owns a z-column of BLOCK_Z = 8 nodes and walks it from the top
+ * down (koff = 7..0, ldc:66), all 512 blocks of 64 threads are resident at once, and inside one koff
+ * iteration the wall branch (ldc:75) precedes the fluid branch (ldc:204) in program order.  With
+ * t(node) = 7 - z % 8 (the koff iteration that processes it):
+ *   t(wall) < t(fluid)                      fresh   (e.g. the z-high wall, and every link with c_z = -1
+ *                                                    unless the fluid node is the top of its column)
+ *   t(wall) > t(fluid)                      stale   (e.g. the z-low wall seen from z = 2)
+ *   equal, same warp (x/8, y/8, z/8, (y%8)/4 equal)   fresh: divergent branches of one warp run in program order
+ *   equal, different warp                   a true race: mode 1 calls it fresh, mode 2 stale
+ * mode 0 is the defined semantics (everything fresh) the product implements. */
+void FN(orc_set_ldc_order)(FN(orc_state) *s, int mode) {
+    s->ldc_order = mode;
+    free(s->stale), free(s->brow);
+    s->stale = NULL, s->brow = NULL;
+    if (!mode || s->case_id != CASE_LDC) return;
+    s->stale = (uint32_t *)calloc((size_t)(s->nfl ? s->nfl : 1), sizeof(uint32_t));
+    s->brow = (int32_t *)malloc((size_t)s->nlat * sizeof(int32_t));
+    for (int i = 0; i < s->nlat; i++) s->brow[i] = -1;
+    for (int b = 0; b < s->nb; b++) s->brow[s->blist[b]] = b;
+    for (int j = 0; j < s->nfl; j++) {
+        size_t c = (size_t)s->cart[s->flist[j]];
+        int x = (int)(c % s->nx), y = (int)((c / s->nx) % s->ny), z = (int)(c / ((size_t)s->nx * s->ny));
+        for (int q = 1; q < 19; q++) {
+            int n = s->pull[(size_t)q * s->nfl + j];
+            if (n < 0 || s->geo[s->cart[n]] != 1) continue;
+            int xs = x - CX[q], ys = y - CY[q], zs = z - CZ[q];
+            int tf = 7 - z % 8, tw = 7 - zs % 8, st;
+            if (tw != tf) st = tw > tf;
+            else if (xs / 8 == x / 8 && ys / 8 == y / 8 && (ys % 8) / 4 == (y % 8) / 4) st = 0;
+            else if (mode == 3) {
+                /* a reader whose own warp holds no wall node at this z skips the wall branch and issues its
+                 * loads at once, ahead of the other warp's bounce; a mixed warp first waits for its own walls */
+                int has_wall = 0;
+                for (int yy = y / 4 * 4; yy < y / 4 * 4 + 4 && yy < s->ny; yy++)
+                    for (int xx = x / 8 * 8; xx < x / 8 * 8 + 8 && xx < s->nx; xx++) has_wall |= s->geo[CIDS(xx, yy, z)] == 1;
+                st = !has_wall;
+            } else st = mode == 2;
+            if (st) s->stale[j] |= 1u << q;
+        }
+    }
+}
 void FN(orc_set_pulse)(FN(orc_state) *s, double amp, double period) {
     s->pulse_amp = amp, s->pulse_period = period;
 }
@@ -536,8 +589,9 @@ void FN(orc_initialize)(FN(orc_state) *s) {
             if (g == 5 || g == 6 || g == 7) s->uz[i] = s->cor_usub;
         }
     }
-    REAL feq[19];
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < nlat; i++) {
+        REAL feq[19];
         if (s->case_id == CASE_LDC) feq_all_ldc_init(s->rho[i], s->ux[i], s->uy[i], s->uz[i], feq);
         else feq_all(s->rho[i], s->ux[i], s->uy[i], s->uz[i], feq);
         for (int q = 0; q < 19; q++) {
@@ -583,6 +637,9 @@ static void update_fluid(FN(orc_state) *s) {
         for (int q = 0; q < 19; q++) {
             int n = s->pull[(size_t)q * nfl + j];
             f[q] = n >= 0 ? s->src[(size_t)q * nlat + n] : R(0.0);
+            /* ldc order model: this launch's wall bounce sits in bscratch until the launch ends */
+            if (s->ldc_order && n >= 0 && s->brow[n] >= 0 && !(s->stale[j] & (1u << q)))
+                f[q] = s->bscratch[(size_t)19 * s->brow[n] + q];
         }
         REAL rho = R(0.0);
         for (int q = 0; q < 19; q++) rho = rho + f[q];
@@ -685,9 +742,11 @@ static void boundary_stream(FN(orc_state) *s) {
     }
 }
 
-/* ldc only: wall bounce on src before the fluid pull (ldc:75-202). */
-static void ldc_wall_bounce_src(FN(orc_state) *s) {
+/* ldc only: wall bounce on src before the fluid pull (ldc:75-202).  phase 1 gathers into bscratch,
+ * phase 2 writes; with an order model (ldc_order != 0) the fluid update runs between the two. */
+static void ldc_wall_bounce_src(FN(orc_state) *s, int phase) {
     const int nlat = s->nlat, nb = s->nb;
+    if (phase != 2) {
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < nb; b++) {
         int i = s->blist[b];
@@ -698,6 +757,8 @@ static void ldc_wall_bounce_src(FN(orc_state) *s) {
         int x = (int)(c % s->nx), y = (int)((c / s->nx) % s->ny), z = (int)(c / ((size_t)s->nx * s->ny));
         wall_gather(s, s->src, x, y, z, 0, out);
     }
+    }
+    if (phase == 1) return;
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < nb; b++) {
         int i = s->blist[b];
@@ -709,8 +770,10 @@ static void ldc_wall_bounce_src(FN(orc_state) *s) {
 /* one iteration of the main loop: ldc:654-666, bif:1249-1257 */
 void FN(orc_step)(FN(orc_state) *s, int nsteps) {
     for (int it = 0; it < nsteps; it++) {
-        if (s->case_id == CASE_LDC) ldc_wall_bounce_src(s);
+        const int ordered = s->case_id == CASE_LDC && s->ldc_order;
+        if (s->case_id == CASE_LDC) ldc_wall_bounce_src(s, ordered ? 1 : 0);
         update_fluid(s);
+        if (ordered) ldc_wall_bounce_src(s, 2);
         boundary_stream(s);
         REAL *t = s->src;
         s->src = s->dst;

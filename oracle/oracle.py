@@ -84,6 +84,7 @@ def _declare(L: C.CDLL) -> None:
         g("orc_set_cor_speeds").argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
         g("orc_set_pulse").argtypes = [C.c_void_p, C.c_double, C.c_double]
         g("orc_set_u_bc").argtypes = [C.c_void_p, C.c_double]
+        g("orc_set_ldc_order").argtypes = [C.c_void_p, C.c_int]
         g("orc_initialize").argtypes = [C.c_void_p]
         g("orc_step").argtypes = [C.c_void_p, C.c_int]
         g("orc_get_fields").argtypes = [C.c_void_p, rp, rp, rp, rp]
@@ -187,6 +188,11 @@ class Oracle:
 
     def set_u_bc(self, u_bc):
         self._fn("orc_set_u_bc")(self._h, float(u_bc))
+
+    def set_ldc_order(self, mode):
+        """0: walls bounce before fluid pulls (defined semantics); 1 / 2: the order ldc.cu's launch executes in,
+        with the truly racy links (same koff iteration, different warp) taken fresh / stale"""
+        self._fn("orc_set_ldc_order")(self._h, int(mode))
 
     def set_pulse(self, amp, period):
         self._fn("orc_set_pulse")(self._h, amp, period)

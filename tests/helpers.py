@@ -50,6 +50,49 @@ def synthetic_openings_mask(nx=40, ny=36, nz=44):
     return flag, rules
 
 
+def stepped_duct_mask(nx=40, ny=24, nz=28):
+    """GEO_OPENINGS mask in which a boundary node has fluid on a TANGENTIAL side: a rectangular duct along x
+    whose ceiling steps up at x = 20; the sub-exit rule labels the low ceiling (z = 14, x <= 19) 5, so the
+    fluid node (20, y, 14) pulls direction (+1,0,0) from the label-5 node (19, y, 14) -- a static link whose
+    source was initialised with a nonzero velocity (cor.cu:302-306)."""
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ztop = np.where(x < 20, 14, 20)
+    flag = ((x >= 3) & (x <= nx - 4) & (y >= 4) & (y <= ny - 5) & (z >= 4) & (z <= ztop)).astype(np.int32)
+    rules = np.array([[0, 3, 1, ny - 2, 1, nz - 2, 1], [0, nx - 4, 1, ny - 2, 1, nz - 2, 2], [2, 14, 6, 19, 6, ny - 7, 4]],
+                     dtype=np.int32)
+    return flag, rules
+
+
+def coronary_like_flag():
+    """A binary voxel field for the UNMODIFIED coronary.cu: its box (291 x 291 x 372, cor:18) and the five
+    opening planes it hard-codes (cor:77-141) -- inlet x = 3, main outlet x = 272, sub-exits capped at
+    z = 185 inside x[217,236] y[113,137], at z = 191 inside x[160,205] y[159,199], and at z = 204.  A main
+    tube along x with three branches rising in +z, each ending exactly on its plane and inside its window.
+    Deterministic formula, no RNG."""
+    nx, ny, nz = 291, 291, 372
+    z, y, x = np.meshgrid(np.arange(nz, dtype=np.float32), np.arange(ny, dtype=np.float32),
+                          np.arange(nx, dtype=np.float32), indexing="ij", sparse=True)
+    zc = 100.0
+    main = ((y - 150.0) ** 2 + (z - zc) ** 2 <= 16.0 ** 2) & (x >= 3) & (x <= 272)
+    b1 = ((x - 226.5) ** 2 + (y - 128.0) ** 2 <= 8.0 ** 2) & (z >= zc) & (z <= 185)
+    b2 = ((x - 182.0) ** 2 + (y - 170.0) ** 2 <= 9.0 ** 2) & (z >= zc) & (z <= 191)
+    b3 = ((x - 100.0) ** 2 + (y - 150.0) ** 2 <= 10.0 ** 2) & (z >= zc) & (z <= 204)
+    return (main | b1 | b2 | b3).astype(np.int32)
+
+
+def write_geo_txt(path, flag, yfast=False):
+    """geo.txt as the reference reads it: "%d " tokens, x fastest (bif:50-61) or y fastest (cor:45-56)"""
+    a = np.ascontiguousarray(flag.transpose(0, 2, 1) if yfast else flag).astype(np.uint8).ravel()
+    out = np.empty((a.size, 2), dtype=np.uint8)
+    out[:, 0] = a + ord("0")
+    out[:, 1] = ord(" ")
+    out.tofile(str(path))
+
+
+def openings_mask(name):
+    return stepped_duct_mask() if name == "corstep" else synthetic_openings_mask()
+
+
 # the reference's own lattice speeds (cor.cu:302-306): 0.1745, 0.1, 0.02 m/s over C_U = 2.74909
 COR_SPEEDS = dict(uin=float(np.float32(0.1745) / np.float32(2.74909090909091)),
                   uout=float(np.float32(0.1) / np.float32(2.74909090909091)),
@@ -78,8 +121,8 @@ def oracle_case(name, n=None, dtype=np.float32, pulse=None, shipped_bc=False):
         o.set_bc_planes(inl, out)
         if pulse:
             o.set_pulse(*pulse)
-    elif name == "cor":
-        flag, rules = synthetic_openings_mask()
+    elif name in ("cor", "corstep"):
+        flag, rules = openings_mask(name)
         geo = O.geo_pre_cor(flag, rules)
         idx, nlat = O.index_transform(geo)
         o = O.Oracle(O.CASE_COR, geo, idx, nlat, TAU_LDC, 0.0, dtype=dtype)
@@ -108,8 +151,8 @@ def gpu_case(name, n=None, precision=None, math_mode=None, pulse=None, shipped_b
         d.nx = d.ny = d.nz = n
     elif name == "bif":
         d = L.case_defaults(L.CASE_GEO_Y_INOUT)
-    elif name == "cor":
-        flag, rules = synthetic_openings_mask()
+    elif name in ("cor", "corstep"):
+        flag, rules = openings_mask(name)
         d = L.case_defaults(L.CASE_GEO_OPENINGS)
         d.nz, d.ny, d.nx = flag.shape
         d.n_openings = len(rules)
@@ -134,8 +177,8 @@ def gpu_case(name, n=None, precision=None, math_mode=None, pulse=None, shipped_b
     c = L.Case(d)
     if name == "bif":
         c.set_flag(bif_flag())
-    if name == "cor":
-        c.set_flag(synthetic_openings_mask()[0])
+    if name in ("cor", "corstep"):
+        c.set_flag(openings_mask(name)[0])
     return c
 
 
