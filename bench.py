@@ -5,10 +5,18 @@
                   [--n 512] [--precision f64|f32] [--storage ab|aa] [--no-e2e] [--no-cpu]
 
 Workload (BASELINE.json configs[2]): dense lid-driven cavity 512^3, fp64, one B200.
-At N > 1 (torchrun, one rank per GPU) the domain is 512 x 512 x (512*N), z-slab sharded, one
-512^3 slab per GPU (weak scaling); the step kernel stores the 5 crossing populations per face cell
-straight into the neighbour GPU's buffer (CUDA IPC peer memory over NVLink); --halo nccl packs and
-sends them with NCCL instead (two-buffer storage only).
+At N > 1 (torchrun, one rank per GPU) the domain is 1024 x 1024 x (128*N), z-slab sharded -- the
+north_star's 1024^2 faces (42 MB per face and direction), 2^27 nodes per GPU like the 512^3 cube, so the
+job is weak-scaled and becomes the 1024^3 box at N = 8.  The step kernel stores the 5 crossing
+populations per face cell straight into the neighbour GPU's buffer (CUDA IPC peer memory over NVLink)
+and the slabs order their steps through progress flags in that memory: the timed loop is
+lbm_slab_step inside the library, no NCCL and no Python per step.  --halo nccl packs and sends the faces
+with NCCL instead (two-buffer storage only).
+
+`parity_check` (untimed, before the timed region): at N = 1 the benchmarked storage and arithmetic
+(in-place, FAST) against the two-buffer storage in the reference's own expression order (STRICT) on the
+benchmarked 512^3 box after the same number of steps; at N > 1 a 64 x 64 x 32N cavity and the bifurcation
+case stepped on the N ranks and on rank 0 alone, compared bit for bit.
 
 A "step" is one pass of the hot path: one fused pull-stream + collide (+ link-wise boundaries)
 launch over every fluid node.  `value` = fluid-node updates / s / 1e6 with all state resident in HBM,
@@ -171,6 +179,18 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     n = args.ref_n
+    if n <= 0:  # the arm's own box when the host can hold it (57 GB in fp64), else the largest cube that fits
+        avail = 0.0
+        try:
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) / 2 ** 20
+        except OSError:
+            pass
+        per_node = (2 * 19 + 4) * (8 if args.precision == "f64" else 4) + 19 * 4 + 12  # two buffers, moments, pull table, masks
+        n = args.n
+        while n > 64 and (n ** 3 * per_node / 2 ** 30 > 0.6 * avail or n ** 3 * (args.steps + args.warmup) > 8e9):
+            n -= 64  # also bounds the run to about a minute of stepping at ~120 MLUPS
     # W warm-up + exactly K timed steps of the bounded sample
     from oracle import oracle as O
 
@@ -183,12 +203,16 @@ def run_reference_arm(args):
     o.step(args.warmup)
     t = o.time_steps(args.steps)
     val = o.num_fluid() * args.steps / t / 1e6
-    sample = f"LDC {n}^3 {args.precision} (bounded sample of the {args.n}^3 workload), {args.steps} steps, oracle port of ldc.cu:57-458"
+    whole = n == args.n and world == 1
+    sample = (f"LDC {n}^3 {args.precision}, {args.steps} steps, oracle port of ldc.cu:57-458 on {threads} host threads: "
+              + ("the arm's whole workload" if whole else f"a bounded sample of the arm's workload (one {args.n}^3-sized share does not fit / is not needed: "
+                                                          "MLUPS of this memory-bound loop is size-independent to first order)"))
+    cfg = workload_config(args, world)
     line = {
         "impl": "reference", "metric": "MLUPS", "value": val, "unit": "MLUPS (fluid-node updates/s/1e6)",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": "MLUPS", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -196,9 +220,138 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def global_dims(args, world):
+    if args.dims:
+        return tuple(args.dims)
+    if world > 1 and args.n == 512:
+        return 1024, 1024, 128 * world  # 1024^2 faces, 2^27 nodes per GPU (north_star: 1024^3 on 8 GPUs)
+    return args.n, args.n, args.n * world
+
+
+def bind_to_gpu_numa_node(local):
+    """run this rank on the cores of the GPU's NUMA node, so that pinned host buffers are first-touched there"""
+    try:
+        import torch
+
+        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def parity_check_single(args, L, prec, local, nfluid_expected):
+    """benchmarked kernel (in-place, FAST) vs two-buffer STRICT on the benchmarked box, same step count"""
+    n, steps = args.n, args.warmup + args.steps
+    fields = {}
+    for name, storage, math in (("bench", {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage], L.MATH_FAST),
+                                ("strict_ab", L.STORE_DENSE_AB, L.MATH_STRICT)):
+        d = L.case_defaults(L.CASE_LDC)
+        d.nx = d.ny = d.nz = n
+        d.z_begin, d.z_end = 0, n
+        d.precision, d.storage, d.math, d.device = prec, storage, math, local
+        c = L.Case(d)
+        c.geo_pre(), c.index_transform(), c.initialize()
+        c.step(steps)
+        fields[name] = c.get_fields()
+        assert c.num_fluid == nfluid_expected
+        c.close()
+        del c
+    scale = max(float(np.abs(a).max()) for a in fields["strict_ab"][1:])
+    err = 0.0
+    for k, (a, b) in enumerate(zip(fields["bench"], fields["strict_ab"])):
+        e = float(np.abs(a - b).max()) / (1.0 if k == 0 else scale)
+        err = max(err, e)
+    tol = 1e-10 if args.precision == "f64" else 2e-4
+    return {"what": f"LDC {n}^3 {args.precision}, {steps} steps: bench storage '{args.storage}' FAST vs two-buffer STRICT "
+                    "(bit-exact with the CPU oracle, tests/test_parity_512_gpu.py); max over rho,ux,uy,uz relative to max|u|",
+            "max_rel_err": err, "tol": tol, "ok": bool(err <= tol)}
+
+
+def parity_check_multi(args, L, slab, prec, rank, world, local):
+    """N ranks == rank 0 alone, bit for bit, on a small cavity and on the bifurcation case"""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    results = {}
+    gold = ROOT / "tests" / "golden"
+    cases = [("ldc_64x64x%d" % (32 * world), L.CASE_LDC, (64, 64, 32 * world), None, None)]
+    if world <= 16 and (gold / "bif_flag_bits.npy").exists():
+        bits = np.load(gold / "bif_flag_bits.npy")
+        flag = np.unpackbits(bits)[: 64 * 83 * 32].astype(np.int32).reshape(32, 83, 64)
+        bc = np.load(gold / "bif_bc.npy")
+        cases.append(("bifurcation_64x83x32", L.CASE_GEO_Y_INOUT, None, flag, (bc[1], bc[2])))
+    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage]
+    for name, rule, dims, flag, planes in cases:
+        def desc(z0, z1):
+            d = L.case_defaults(rule)
+            if dims:
+                d.nx, d.ny, d.nz = dims
+            d.z_begin, d.z_end = (0, d.nz) if z0 is None else (z0, z1)
+            d.precision, d.storage, d.math, d.device = prec, storage, L.MATH_FAST, local
+            return d
+
+        nz = desc(None, None).nz
+        z0, z1 = slab.slab_ranges(nz, world)[rank]
+        c = slab.SlabCase(desc(z0, z1))
+        c.setup(flag=flag, bc_planes=planes)
+        fused = args.halo == "p2p" and c.enable_p2p()
+        steps = 41
+        c.step(steps)
+        mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
+        cnt = torch.tensor([mine[0].numel()], dtype=torch.int64, device="cuda")
+        counts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        counts = [int(t.item()) for t in counts]
+        same = True
+        ref = None
+        if rank == 0:
+            one = L.Case(desc(None, None))
+            if flag is not None:
+                one.set_flag(flag)
+            one.geo_pre(), one.index_transform()
+            if planes is not None:
+                one.set_bc_planes(*planes)
+            one.initialize()
+            one.step(steps)
+            ref = one.get_fields()
+            one.close()
+        for k in range(4):
+            parts = []
+            for r in range(world):
+                buf = mine[k] if r == rank else torch.zeros(counts[r], dtype=mine[k].dtype, device="cuda")
+                if counts[r]:
+                    dist.broadcast(buf, r)
+                parts.append(buf)
+            if rank == 0:
+                same = same and bool(np.array_equal(torch.cat(parts).cpu().numpy(), ref[k]))
+        c.close()
+        results[name] = {"bitwise_equal": same if rank == 0 else None, "steps": steps, "fused_exchange": bool(fused),
+                         "nlattice": int(sum(counts))}
+        dist.barrier()
+    ok = all(v["bitwise_equal"] for v in results.values()) if rank == 0 else True
+    return {"what": f"{world} ranks (z-slabs, storage '{args.storage}', FAST {args.precision}) vs the same case on rank 0 alone, rho,ux,uy,uz compared bit for bit",
+            "cases": results, "ok": bool(ok)}
+
+
 def workload_config(args, world):
     n = args.n
-    gx, gy, gz = (n, n, n * world) if not args.dims else args.dims
+    gx, gy, gz = global_dims(args, world)
     return {"workload": f"dense lid-driven cavity {gx}x{gy}x{gz} D3Q19 BGK {args.precision}, tau=0.55, Re~222 (ldc.cu rules), "
                         f"z-slabs of {gz // world} planes per GPU",
             "storage": args.storage, "math": "fast", "bytes_per_node_update": BYTES_PER_LU[args.precision],
@@ -215,6 +368,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
 
@@ -224,8 +378,11 @@ def run_ours(args):
     storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage]
     dtype = np.float64 if args.precision == "f64" else np.float32
 
-    gnx, gny, gnz = (n, n, n * world) if not args.dims else args.dims
+    gnx, gny, gnz = global_dims(args, world)
     z_lo, z_hi = slab.slab_ranges(gnz, world)[rank]
+    parity = None
+    if not args.no_parity and world > 1:
+        parity = parity_check_multi(args, L, slab, prec, rank, world, local)
 
     def build_case():
         d = L.case_defaults(L.CASE_LDC)
@@ -257,6 +414,11 @@ def run_ours(args):
     c = setup(build_case())
     nfluid_local = c.num_fluid
     nfluid = nfluid_local
+    if not args.no_parity and world == 1 and not args.dims:
+        c.close()
+        del c
+        parity = parity_check_single(args, L, prec, local, nfluid_local)
+        c = setup(build_case())
     if world > 1:
         t_ = torch.tensor([nfluid_local], dtype=torch.int64, device="cuda")
         dist.all_reduce(t_)
@@ -315,7 +477,7 @@ def run_ours(args):
         c.get_fields(outs)
         barrier()
         t_e2e = time.perf_counter() - t0
-        phases = {"setup_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": time.perf_counter() - t2}
+        phases = {"setup_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": time.perf_counter() - t2, "numa_node": numa}
         if world > 1:
             t_ = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
@@ -346,7 +508,7 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "kernel": "k_step_dense", "algorithmic_bytes_per_launch": nfluid_local * bpl,
                          "frac_of_spec_8TBs": achieved / 8000.0},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_check": parity,
             "wall_ms_per_step": wall / args.steps * 1e3, "fluid_nodes": int(nfluid),
             "mlups_all_nodes": value * (gnx * gny * gnz) / nfluid,
         }
@@ -376,10 +538,11 @@ def main():
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: peer stores fused into the step kernel, or pack + NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity_check")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=25)
-    ap.add_argument("--ref-n", type=int, default=224)
+    ap.add_argument("--ref-n", type=int, default=0, help="cube edge of the CPU reference arm (0: the arm's own n when host memory allows)")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram__bytes_read.sum+dram__bytes_write.sum per launch from the committed ncu capture")
     args = ap.parse_args()

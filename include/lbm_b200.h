@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 typedef struct lbm_solver_s *lbm_handle;
 
@@ -281,6 +281,53 @@ int lbm_p2p_open(const lbm_ipc_handle *handle, void **dev_ptr);
 int lbm_p2p_close(void *dev_ptr);
 int lbm_p2p_attach(lbm_handle h, int32_t side, void *peer_a, void *peer_b, int64_t peer_qstride, int64_t peer_halo_c0,
                    int64_t peer_face_c0);
+
+/* ---- a slab's time loop entirely inside the library ----
+ * lbm_slab_step runs n steps of a z-slab with nothing but kernel launches on the host: the crossing
+ * populations travel by the fused peer stores above and the ORDERING with the two neighbours (a slab may
+ * touch the planes it shares with a neighbour only after that neighbour finished the face launches of the
+ * previous step) is decided on the device -- no global barrier, no NCCL, no host thread in the loop.
+ * Between processes (one rank per GPU) the neighbours report their progress into a small sync block in
+ * this slab's memory: lbm_sync_export publishes it like lbm_p2p_export publishes the buffers,
+ * lbm_sync_attach(side, pointer to the NEIGHBOUR's block as mapped here by lbm_p2p_open) connects one
+ * side; attach on every slab before any of them steps again (it also restarts the step count the two
+ * sides compare, so repeat it after lbm_checkpoint_load).  A wait that sees no progress for 20 s gives up
+ * and the call returns LBM_ERR_CUDA instead of hanging the device.
+ * flags_last: LBM_STEP_MOMENTS materialises rho,u on the last step.  S_out (optional, n doubles) receives
+ * this slab's share of S = sum|u| of every step (ldc.cu:660-662); the caller all-reduces it. */
+int lbm_slab_step(lbm_handle h, int32_t n, int32_t flags_last, double *S_out, float *elapsed_ms);
+int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset);
+int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync);
+
+/* ---- several z-slabs driven from ONE process: the multi-GPU form of the reference's main() ----
+ * (SURVEY 8b `lbm_create_distributed`; the reference is single-GPU, ldc.cu:612-717.)
+ * nslabs contiguous z ranges of desc's box, slab r on CUDA device devices[r] (NULL: r modulo the device
+ * count; several slabs may share a device).  lbm_group_setup = geo_pre, index_transform (numbering
+ * continued across slabs: bif:241-252), read_vel, initialize on every slab, then peer access + fused
+ * peer-store exchange + event ordering between neighbours.  flag_cartesian / the bc planes are optional
+ * (NULL: geo_path / bc_path as in the single-domain calls).  The run loops and writers below are the
+ * single-domain ones with "all-reduced" reductions: S and sum(u^2) are the sums of the slabs' shares. */
+typedef struct lbm_group_s *lbm_group;
+int lbm_create_distributed(const lbm_case_desc *desc, int32_t nslabs, const int32_t *devices, lbm_group *out);
+int lbm_group_destroy(lbm_group g);
+const char *lbm_group_last_error(lbm_group g); /* g may be NULL: last lbm_create_distributed error */
+int32_t lbm_group_size(lbm_group g);
+lbm_handle lbm_group_slab(lbm_group g, int32_t r); /* the r-th slab's handle (owned by the group) */
+int lbm_group_setup(lbm_group g, const int32_t *flag_cartesian, const float *inlet_uy, const float *outlet_uy,
+                    int64_t *nlattice);
+int lbm_group_step(lbm_group g, int32_t n, float *elapsed_ms); /* ms: host clock around the synchronised loop */
+int64_t lbm_group_num_fluid(lbm_group g);
+int lbm_group_residual(lbm_group g, int32_t kind, double *value);
+int lbm_group_get_fields(lbm_group g, void *rho, void *ux, void *uy, void *uz); /* NLATTICE entries each */
+int lbm_group_get_index(lbm_group g, int32_t *index_cartesian);                 /* whole box */
+int lbm_group_set_output_format(lbm_group g, int32_t format);
+int lbm_group_output_save(lbm_group g, int32_t t); /* ASCII: ONE file, byte-identical to the single-domain one */
+int lbm_group_run_fixed(lbm_group g, int32_t repeat, int32_t time_save, int32_t write_files);
+int lbm_group_run_converge(lbm_group g, int32_t max_it, double tol, int32_t stag_max, int32_t time_save,
+                           int32_t write_files, int32_t *iterations, double *residual);
+
+/* write_once(): cor.cu:1033-1051 -- "x,y,z,ux,uy,uz" (%f) of every inlet / outlet node (labels 2,3,5,6,7) */
+int lbm_write_bc_csv(lbm_handle h, const char *path);
 
 /* cudaStream_t of the handle as an opaque pointer (for event / NCCL interop) */
 void *lbm_stream(lbm_handle h);

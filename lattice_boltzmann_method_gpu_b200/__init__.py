@@ -3,4 +3,4 @@ interface of Xinhuan-Imperial/Lattice-Boltzmann-Method-GPU.  All compute lives i
 library (csrc/ -> liblbm_b200.so); this package is the ctypes host mirror of the reference's
 geo_pre / index_transform / read_vel / initialize / update / outputSave sequence."""
 from .api import *  # noqa: F401,F403
-from .api import Case, CaseDesc, LbmError, load_library, make_case, case_defaults, p2p_open, voxelize, ABI_SYMBOLS, LIB_PATH  # noqa: F401
+from .api import Case, Group, CaseDesc, LbmError, load_library, make_case, case_defaults, p2p_open, voxelize, ABI_SYMBOLS, LIB_PATH  # noqa: F401

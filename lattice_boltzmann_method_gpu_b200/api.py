@@ -20,7 +20,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "liblbm_b200.so"
+# LBM_B200_LIB selects another build of the same library (the self-checking one, tools/selfcheck.py)
+LIB_PATH = Path(os.environ["LBM_B200_LIB"]) if os.environ.get("LBM_B200_LIB") else PKG / "liblbm_b200.so"
 
 # enums of include/lbm_b200.h
 CASE_LDC, CASE_POISEUILLE, CASE_GEO_Y_INOUT, CASE_GEO_OPENINGS = 0, 1, 2, 3
@@ -78,6 +79,11 @@ ABI_SYMBOLS = [
     "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_voxelize_stl", "lbm_voxelize_triangles", "lbm_voxel_last_error", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
     "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
+    "lbm_slab_step", "lbm_sync_export", "lbm_sync_attach", "lbm_write_bc_csv",
+    "lbm_create_distributed", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size", "lbm_group_slab",
+    "lbm_group_setup", "lbm_group_step", "lbm_group_num_fluid", "lbm_group_residual", "lbm_group_get_fields",
+    "lbm_group_get_index", "lbm_group_set_output_format", "lbm_group_output_save", "lbm_group_run_fixed",
+    "lbm_group_run_converge",
 ]
 
 _lib = None
@@ -146,6 +152,25 @@ def load_library() -> C.CDLL:
         "lbm_checkpoint_load": ([vp, C.c_char_p], C.c_int),
         "lbm_stream": ([vp], vp),
         "lbm_sync": ([vp], C.c_int),
+        "lbm_slab_step": ([vp, i32, i32, vp, P(C.c_float)], C.c_int),
+        "lbm_sync_export": ([vp, vp, P(vp), P(i64)], C.c_int),
+        "lbm_sync_attach": ([vp, i32, vp], C.c_int),
+        "lbm_write_bc_csv": ([vp, C.c_char_p], C.c_int),
+        "lbm_create_distributed": ([P(CaseDesc), i32, vp, P(vp)], C.c_int),
+        "lbm_group_destroy": ([vp], C.c_int),
+        "lbm_group_last_error": ([vp], C.c_char_p),
+        "lbm_group_size": ([vp], i32),
+        "lbm_group_slab": ([vp, i32], vp),
+        "lbm_group_setup": ([vp, vp, vp, vp, P(i64)], C.c_int),
+        "lbm_group_step": ([vp, i32, P(C.c_float)], C.c_int),
+        "lbm_group_num_fluid": ([vp], i64),
+        "lbm_group_residual": ([vp, i32, P(dbl)], C.c_int),
+        "lbm_group_get_fields": ([vp, vp, vp, vp, vp], C.c_int),
+        "lbm_group_get_index": ([vp, vp], C.c_int),
+        "lbm_group_set_output_format": ([vp, i32], C.c_int),
+        "lbm_group_output_save": ([vp, i32], C.c_int),
+        "lbm_group_run_fixed": ([vp, i32, i32, i32], C.c_int),
+        "lbm_group_run_converge": ([vp, i32, dbl, i32, i32, i32, P(i32), P(dbl)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -302,6 +327,28 @@ class Case:
     def p2p_attach(self, side: int, peer_a, peer_b, peer_qstride: int = 0, peer_halo_c0: int = 0, peer_face_c0: int = 0):
         self._ck(self._L.lbm_p2p_attach(self._h, side, peer_a, peer_b, peer_qstride, peer_halo_c0, peer_face_c0))
 
+    # -- the slab's time loop inside the library (neighbours ordered on the device)
+    def sync_export(self):
+        """dict: IPC handle of this slab's sync block, its raw pointer and byte offset inside its allocation"""
+        handle = (C.c_ubyte * 64)()
+        ptr, boff = C.c_void_p(), C.c_int64()
+        self._ck(self._L.lbm_sync_export(self._h, handle, C.byref(ptr), C.byref(boff)))
+        return {"handle": bytes(handle), "ptr": ptr.value, "boff": boff.value}
+
+    def sync_attach(self, side: int, peer_sync):
+        self._ck(self._L.lbm_sync_attach(self._h, side, peer_sync))
+
+    def slab_step(self, n: int, moments_last: bool = True, velsum: bool = False):
+        """n steps; returns (elapsed ms measured with CUDA events on the slab's stream, S per step or None)"""
+        S = np.zeros(int(n), dtype=np.float64) if velsum else None
+        ms = C.c_float()
+        self._ck(self._L.lbm_slab_step(self._h, int(n), STEP_MOMENTS if moments_last else 0,
+                                       S.ctypes.data if velsum else None, C.byref(ms)))
+        return ms.value, S
+
+    def write_bc_csv(self, path):
+        self._ck(self._L.lbm_write_bc_csv(self._h, os.fsencode(str(path))))
+
     def residual(self, kind: int = RES_VELSUM) -> float:
         v = C.c_double()
         self._ck(self._L.lbm_residual(self._h, kind, C.byref(v)))
@@ -380,6 +427,93 @@ class Case:
     @property
     def stream(self) -> int:
         return self._L.lbm_stream(self._h)
+
+
+class Group:
+    """Several z-slabs of one case driven from this process (`lbm_create_distributed`): the multi-GPU
+    form of the reference's main().  devices=None puts slab r on device r modulo the device count;
+    repeating a device gives several slabs on one GPU."""
+
+    def __init__(self, desc: CaseDesc, nslabs: int, devices=None):
+        self._L = load_library()
+        desc.struct_size = C.sizeof(CaseDesc)
+        self.desc = desc
+        self.dtype = np.dtype(np.float64 if desc.precision == F64 else np.float32)
+        self._g = C.c_void_p()
+        dev = None if devices is None else (C.c_int32 * nslabs)(*[int(v) for v in devices])
+        rc = self._L.lbm_create_distributed(C.byref(desc), int(nslabs), dev, C.byref(self._g))
+        if rc:
+            raise LbmError(rc, self._L.lbm_group_last_error(None).decode())
+        self.nlattice = None
+
+    def _ck(self, rc):
+        if rc:
+            raise LbmError(rc, self._L.lbm_group_last_error(self._g).decode())
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            self._L.lbm_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return self._L.lbm_group_size(self._g)
+
+    def setup(self, flag=None, bc_planes=None) -> int:
+        n = C.c_int64()
+        f = None if flag is None else np.ascontiguousarray(flag, dtype=np.int32)
+        a = b = None
+        if bc_planes is not None:
+            a = np.ascontiguousarray(bc_planes[0], dtype=np.float32)
+            b = np.ascontiguousarray(bc_planes[1], dtype=np.float32)
+        self._ck(self._L.lbm_group_setup(self._g, None if f is None else f.ctypes.data, None if a is None else a.ctypes.data,
+                                         None if b is None else b.ctypes.data, C.byref(n)))
+        self.nlattice = n.value
+        return n.value
+
+    def step(self, n: int = 1) -> float:
+        ms = C.c_float()
+        self._ck(self._L.lbm_group_step(self._g, int(n), C.byref(ms)))
+        return ms.value
+
+    @property
+    def num_fluid(self) -> int:
+        return self._L.lbm_group_num_fluid(self._g)
+
+    def residual(self, kind: int = RES_VELSUM) -> float:
+        v = C.c_double()
+        self._ck(self._L.lbm_group_residual(self._g, kind, C.byref(v)))
+        return v.value
+
+    def get_fields(self):
+        out = [np.empty(self.nlattice, dtype=self.dtype) for _ in range(4)]
+        self._ck(self._L.lbm_group_get_fields(self._g, *[o.ctypes.data for o in out]))
+        return out
+
+    def get_index(self) -> np.ndarray:
+        g = np.empty((self.desc.nz, self.desc.ny, self.desc.nx), dtype=np.int32)
+        self._ck(self._L.lbm_group_get_index(self._g, g.ctypes.data))
+        return g
+
+    def set_output_format(self, fmt: int):
+        self._ck(self._L.lbm_group_set_output_format(self._g, fmt))
+
+    def outputSave(self, t: int):
+        self._ck(self._L.lbm_group_output_save(self._g, int(t)))
+
+    def run_fixed(self, repeat: int, time_save: int, write_files: bool = True):
+        self._ck(self._L.lbm_group_run_fixed(self._g, repeat, time_save, int(write_files)))
+
+    def run_converge(self, max_it=10000, tol=1e-6, stag_max=50, time_save=500, write_files=True):
+        its, res = C.c_int32(), C.c_double()
+        self._ck(self._L.lbm_group_run_converge(self._g, max_it, tol, stag_max, time_save, int(write_files), C.byref(its), C.byref(res)))
+        return its.value, res.value
 
 
 _opened_ipc = {}  # handle bytes -> [mapped pointer, reference count]

@@ -54,12 +54,27 @@ struct SolverBase {
     virtual int step_interior() = 0;
     virtual int step_end() = 0;
     virtual int last_velsum(double *v) = 0;
+    // n steps of a z-slab with every ordering decision on the device (flags in peer memory across
+    // processes, events inside one process); S_out (optional, n doubles): this slab's share of sum|u| per step
+    virtual int slab_steps(int n, int flags_last, double *S_out, float *ms) = 0;
+    virtual int sync_export(lbm_ipc_handle *h, void **ptr, int64_t *boff) = 0;
+    virtual int sync_attach(int side, void *peer_sync) = 0;
+    virtual void set_inproc_neighbour(int side, SolverBase *nb) = 0;
+    virtual cudaEvent_t face_event(int k) = 0;
+    virtual int enqueue_step(int flags, double *acc_slot) = 0;  // begin + interior + end, no host sync
+    virtual int fetch_acc(int first, int n, double *out) = 0;
+    virtual int zero_acc(int first, int n) = 0;
+    virtual double *acc_slot(int k) = 0;
+    virtual int write_global(int t, const int32_t *index_global, const void *rho, const void *ux, const void *uy,
+                             const void *uz, int64_t nlattice) = 0;
+    bool lo_halo_b = false, hi_halo_b = false;
     virtual int residual(int kind, double *v) = 0;
     virtual int get_geo(int32_t *g) = 0;
     virtual int get_index(int32_t *g) = 0;
     virtual int get_fields(void *rho, void *ux, void *uy, void *uz, int64_t *first, int64_t *count) = 0;
     virtual int get_populations(void *f) = 0;
     virtual int output_save(int t) = 0;
+    virtual int write_bc_csv(const char *path) = 0;
     int out_format = LBM_OUT_ASCII_VTK;
     virtual int run_fixed(int repeat, int time_save, int write_files) = 0;
     virtual int run_converge(int max_it, double tol, int stag_max, int time_save, int write_files, int *its,
@@ -125,13 +140,21 @@ struct Solver final : SolverBase {
     size_t scratch_ints = 0;
     double last_S = 0.0;
     std::vector<long long> plane_first;  // [planes of the state box + 1] global compact id each plane starts at
-    T *d_stage = nullptr;                // staging of get_fields (dense storage), one plane group at a time
+    T *d_stage = nullptr;                // staging of get_fields (dense storage), two plane groups in flight
     size_t stage_elems = 0;
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_gathered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     long long pend_i0 = 0, pend_i1 = 0;
     bool interior_pending = false;
     // fused peer-to-peer halo exchange (per side: neighbour's two buffers, q stride, halo offset)
     T *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     long long peer_qs[2] = {0, 0}, peer_c0[2] = {0, 0}, peer_own[2] = {0, 0};
+    // neighbour ordering of slab steps: flags in peer memory (other process) or events (same process)
+    unsigned long long *d_sync = nullptr;               // [0] low neighbour's progress, [1] high neighbour's, [2] timeout
+    unsigned long long *peer_sync[2] = {nullptr, nullptr};  // where this slab reports its own progress, per side
+    int64_t sync_base = 0;                              // step count at which the progress counters were zero
+    cudaEvent_t ev_face[2] = {nullptr, nullptr};        // recorded after the face launches of even / odd steps
+    SolverBase *inproc_nb[2] = {nullptr, nullptr};
     // sparse storage (reference compact order + run segments)
     bool sparse = false;
     long long n_lo_stored = 0, stored_box = 0;   // stored nodes of the low halo plane / of the whole state box
@@ -154,8 +177,16 @@ struct Solver final : SolverBase {
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
+        fr(d_sync);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto &e : ev_face)
+            if (e) cudaEventDestroy(e);
+        for (int k = 0; k < 2; k++) {
+            if (ev_gathered[k]) cudaEventDestroy(ev_gathered[k]);
+            if (ev_copied[k]) cudaEventDestroy(ev_copied[k]);
+        }
+        if (st_copy) cudaStreamDestroy(st_copy);
         if (st) cudaStreamDestroy(st);
     }
 
@@ -202,9 +233,11 @@ struct Solver final : SolverBase {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0));
         CK(cudaEventCreate(&ev1));
+        for (auto &e : ev_face) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         fluid_label = d.case_rule == LBM_CASE_LDC ? 3 : 4;
         own_z0 = d.z_begin, own_z1 = d.z_end;
         lo_halo = own_z0 > 0, hi_halo = own_z1 < d.nz;
+        lo_halo_b = lo_halo, hi_halo_b = hi_halo;
         const int px = ((d.nx + 31) / 32) * 32;
         box.nx = d.nx, box.ny = d.ny, box.nz = d.nz, box.px = px, box.plane = (long long)px * d.ny;
         box.z0 = own_z0 - (lo_halo ? 1 : 0), box.z1 = own_z1 + (hi_halo ? 1 : 0);
@@ -229,7 +262,8 @@ struct Solver final : SolverBase {
             bc[s.label] = BcEntry{s.kind, s.normal_axis, s.normal_sign, s.vel_axis, s.source, s.pulsatile, s.value,
                                   s.init_value};
         }
-        if (dalloc(&d_acc, ACC_SLOTS) || dalloc(&d_cnt, 8)) return LBM_ERR_NOMEM;
+        if (dalloc(&d_acc, ACC_SLOTS) || dalloc(&d_cnt, 8) || dalloc(&d_sync, 8)) return LBM_ERR_NOMEM;
+        CK(cudaMemset(d_sync, 0, 8 * sizeof(unsigned long long)));
         return 0;
     }
 
@@ -497,7 +531,14 @@ struct Solver final : SolverBase {
         d_cur = d_fa, d_nxt = d_fb;
         steps = 0;
         have_init = true, have_moments = false, in_step = false;
+        detach_neighbours();
         return 0;
+    }
+    // a freshly initialised slab has no ordering with its neighbours yet (lbm_sync_attach / the group wire it)
+    void detach_neighbours() {
+        peer_sync[0] = peer_sync[1] = nullptr;
+        inproc_nb[0] = inproc_nb[1] = nullptr;
+        sync_base = 0;
     }
 
     long long count_plane(int zl) {
@@ -585,6 +626,7 @@ struct Solver final : SolverBase {
         d_cur = d_fa, d_nxt = d_fb;
         steps = 0;
         have_init = true, have_moments = false, in_step = false;
+        detach_neighbours();
         return 0;
     }
 
@@ -672,21 +714,35 @@ struct Solver final : SolverBase {
     }
 
     // one step with an optional velsum slot; used by run_converge and the slab protocol
-    int step_begin(int flags) override {
+    double *step_acc = nullptr;
+    bool step_nosync = false;
+    static constexpr unsigned long long SYNC_TIMEOUT_NS = 20ull * 1000000000ull;
+    int step_begin(int flags) override { return step_begin_ex(flags, nullptr); }
+    int step_begin_ex(int flags, double *acc) {
         if (!have_init) FAIL(LBM_ERR_STATE, "step before initialize");
         if (in_step) FAIL(LBM_ERR_STATE, "lbm_step_begin called twice");
         CK(cudaSetDevice(d.device));
         const bool mom = flags & LBM_STEP_MOMENTS, res = flags & LBM_STEP_VELSUM;
-        if (d.storage == LBM_STORE_DENSE_AA && ((lo_halo && !peer_buf[0][0]) || (hi_halo && !peer_buf[1][0])))
+        if (in_place() && ((lo_halo && !peer_buf[0][0]) || (hi_halo && !peer_buf[1][0])))
             FAIL(LBM_ERR_STATE, "in-place storage exchanges slab faces by peer stores only: call lbm_p2p_attach first");
         step_flags = flags;
-        if (res) CK(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
+        step_acc = acc ? acc : d_acc, step_nosync = acc != nullptr;
+        if (res && !acc) CK(cudaMemsetAsync(d_acc, 0, sizeof(double), st));
+        // a slab may touch the planes it shares with a neighbour only after that neighbour finished the
+        // face launches of the previous step (flags across processes, events inside one)
+        const unsigned long long done = (unsigned long long)(steps - sync_base);
+        if (peer_sync[0] || peer_sync[1]) {
+            CK(launch_slab_wait(d_sync, peer_sync[0] ? done : 0ull, peer_sync[1] ? done : 0ull, SYNC_TIMEOUT_NS, st));
+            launches++;
+        }
+        for (int sd = 0; sd < 2; sd++)
+            if (inproc_nb[sd]) CK(cudaStreamWaitEvent(st, inproc_nb[sd]->face_event((int)((steps + 1) & 1)), 0));
         int r;
         const int zt = own_z1 - 1, zb = own_z0;
         long long i0 = plane_c(own_z0), i1 = plane_c(own_z1);
         if (hi_halo) {
             const int sides = 2 | ((lo_halo && zb == zt) ? 1 : 0);
-            if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, d_acc, sides))) return r;
+            if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, step_acc, sides))) return r;
             if (!peer_buf[1][0]) {
                 if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[1], face_n[1], 1, d_send[1], face_n[1], st));
                 else CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
@@ -695,7 +751,7 @@ struct Solver final : SolverBase {
             i1 = plane_c(zt);
         }
         if (lo_halo && !(hi_halo && zb == zt)) {
-            if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, d_acc, 1))) return r;
+            if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, step_acc, 1))) return r;
             i0 = plane_c(zb + 1);
         }
         if (lo_halo && !peer_buf[0][0]) {
@@ -703,6 +759,11 @@ struct Solver final : SolverBase {
             else CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
             launches++;
         }
+        if (peer_sync[0] || peer_sync[1]) {
+            CK(launch_slab_signal(peer_sync[0], peer_sync[1], done + 1ull, st));
+            launches++;
+        }
+        if (inproc_nb[0] || inproc_nb[1]) CK(cudaEventRecord(ev_face[steps & 1], st));
         pend_i0 = i0, pend_i1 = i1, interior_pending = true;
         in_step = true;
         return 0;
@@ -714,7 +775,7 @@ struct Solver final : SolverBase {
         if (!interior_pending) return 0;
         CK(cudaSetDevice(d.device));
         interior_pending = false;
-        return launch_range(pend_i0, pend_i1, step_flags & LBM_STEP_MOMENTS, step_flags & LBM_STEP_VELSUM, d_acc);
+        return launch_range(pend_i0, pend_i1, step_flags & LBM_STEP_MOMENTS, step_flags & LBM_STEP_VELSUM, step_acc);
     }
     int step_end() override {
         if (!in_step) FAIL(LBM_ERR_STATE, "lbm_step_end without lbm_step_begin");
@@ -733,7 +794,7 @@ struct Solver final : SolverBase {
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
             launches++;
         }
-        if (step_flags & LBM_STEP_VELSUM) {
+        if ((step_flags & LBM_STEP_VELSUM) && !step_nosync) {
             CK(cudaMemcpyAsync(&last_S, d_acc, sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
@@ -741,6 +802,112 @@ struct Solver final : SolverBase {
         std::swap(d_cur, d_nxt);
         steps++;
         in_step = false;
+        return 0;
+    }
+    bool in_place() const { return d.storage == LBM_STORE_DENSE_AA; }
+    int enqueue_step(int flags, double *acc) override {
+        int r = step_begin_ex(flags, acc);
+        if (r) return r;
+        if ((r = step_interior())) return r;
+        return step_end();
+    }
+    double *acc_slot(int k) override { return d_acc + 2 + (k % (ACC_SLOTS - 2)); }
+    int zero_acc(int first, int n) override {
+        CK(cudaSetDevice(d.device));
+        CK(cudaMemsetAsync(d_acc + 2 + first, 0, sizeof(double) * (size_t)n, st));
+        return 0;
+    }
+    int fetch_acc(int first, int n, double *out) override {
+        CK(cudaSetDevice(d.device));
+        CK(cudaMemcpyAsync(out, d_acc + 2 + first, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return check_sync_error();
+    }
+    int check_sync_error() {
+        if (!peer_sync[0] && !peer_sync[1]) return 0;
+        unsigned long long flag = 0;
+        CK(cudaMemcpyAsync(&flag, d_sync + 2, sizeof flag, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (flag) FAIL(LBM_ERR_CUDA, "a neighbouring slab did not report its step within %.0f s", SYNC_TIMEOUT_NS * 1e-9);
+        return 0;
+    }
+    cudaEvent_t face_event(int k) override { return ev_face[k & 1]; }
+    void set_inproc_neighbour(int side, SolverBase *nb) override { inproc_nb[side] = nb; }
+    // lbm_slab_step: n steps of this slab, neighbours ordered on the device, nothing but launches on the host
+    int slab_steps(int n, int flags_last, double *S_out, float *ms) override {
+        if (!have_init) FAIL(LBM_ERR_STATE, "step before initialize");
+        if (n < 0) FAIL(LBM_ERR_ARG, "negative step count");
+        for (int sd = 0; sd < 2; sd++) {
+            if (!(sd == 0 ? lo_halo : hi_halo)) continue;
+            if (!peer_buf[sd][0]) FAIL(LBM_ERR_STATE, "lbm_slab_step needs the fused peer-store exchange: lbm_p2p_attach side %d first", sd);
+            if (!peer_sync[sd] && !inproc_nb[sd])
+                FAIL(LBM_ERR_STATE, "lbm_slab_step: no ordering with the neighbour on side %d (lbm_sync_attach)", sd);
+        }
+        CK(cudaSetDevice(d.device));
+        if (ms) CK(cudaEventRecord(ev0, st));
+        const int nslots = ACC_SLOTS - 2;
+        for (int i0 = 0; i0 < n; i0 += nslots) {
+            const int nb = std::min(nslots, n - i0);
+            if (S_out) CK(cudaMemsetAsync(d_acc + 2, 0, sizeof(double) * (size_t)nb, st));
+            for (int j = 0; j < nb; j++) {
+                const int flags = (i0 + j == n - 1 ? (flags_last & LBM_STEP_MOMENTS) : 0) | (S_out ? LBM_STEP_VELSUM : 0);
+                int r = enqueue_step(flags, S_out ? d_acc + 2 + j : d_acc + 1);
+                if (r) return r;
+            }
+            if (S_out) {
+                CK(cudaMemcpyAsync(S_out + i0, d_acc + 2, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+        if (ms) {
+            CK(cudaEventRecord(ev1, st));
+            CK(cudaEventSynchronize(ev1));
+            CK(cudaEventElapsedTime(ms, ev0, ev1));
+        } else {
+            CK(cudaStreamSynchronize(st));
+        }
+        return check_sync_error();
+    }
+    int sync_export(lbm_ipc_handle *h, void **ptr, int64_t *boff) override {
+        CK(cudaSetDevice(d.device));
+        if (h) {
+            cudaIpcMemHandle_t ih;
+            CK(cudaIpcGetMemHandle(&ih, d_sync));
+            memset(h, 0, sizeof(lbm_ipc_handle));
+            memcpy(h, &ih, sizeof ih);
+        }
+        if (ptr) *ptr = d_sync;
+        if (boff) {
+            int r = alloc_offset(d_sync, boff);
+            if (r) return r;
+        }
+        return 0;
+    }
+    // peer_sync: the NEIGHBOUR's sync block as mapped into this process (null detaches).  Collective in
+    // effect: both sides reset their counters here, so attach on all slabs before any of them steps.
+    int sync_attach(int side, void *peer) override {
+        if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
+        if (!(side == 0 ? lo_halo : hi_halo)) FAIL(LBM_ERR_ARG, "no neighbour on side %d", side);
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(st));
+        // this slab is the HIGH neighbour of the slab below it and the LOW neighbour of the one above
+        peer_sync[side] = peer ? (unsigned long long *)peer + (side == 0 ? 1 : 0) : nullptr;
+        CK(cudaMemsetAsync(d_sync + side, 0, sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(d_sync + 2, 0, sizeof(unsigned long long), st));
+        CK(cudaStreamSynchronize(st));
+        sync_base = steps;
+        return 0;
+    }
+    // byte offset of a device pointer inside the cudaMalloc block its IPC handle stands for
+    int alloc_offset(const void *p, int64_t *off) {
+        typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+        unsigned long long base = 0;
+        size_t sz = 0;
+        if (!fn || ((range_fn)fn)(&base, &sz, (unsigned long long)(uintptr_t)p) != 0) FAIL(LBM_ERR_CUDA, "cuMemGetAddressRange failed");
+        *off = (int64_t)((unsigned long long)(uintptr_t)p - base);
         return 0;
     }
     int last_velsum(double *v) override {
@@ -882,17 +1049,8 @@ struct Solver final : SolverBase {
             }
             if (ptrs) ptrs[k] = bufs[k];
             if (boff) {
-                // offset of the buffer inside the allocation the IPC handle stands for (driver entry point
-                // fetched at run time: no link-time dependency on libcuda)
-                typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
-                void *fn = nullptr;
-                cudaDriverEntryPointQueryResult qr;
-                CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
-                unsigned long long base = 0;
-                size_t sz = 0;
-                if (!fn || ((range_fn)fn)(&base, &sz, (unsigned long long)(uintptr_t)bufs[k]) != 0)
-                    FAIL(LBM_ERR_CUDA, "cuMemGetAddressRange failed");
-                boff[k] = (int64_t)((unsigned long long)(uintptr_t)bufs[k] - base);
+                int r = alloc_offset(bufs[k], &boff[k]);
+                if (r) return r;
             }
         }
         if (qs) *qs = qstride;
@@ -973,33 +1131,63 @@ struct Solver final : SolverBase {
             if (count) *count = stored_own;
             return 0;
         }
-        // dense storage: gather into compact order one group of planes at a time through a small
-        // persistent staging buffer (the kernel is ~1 % of the D2H copy time)
-        const long long group_cells = 32LL << 20;
+        if (store_all()) {
+            // every node of the box is stored (ldc.cu:54): the moment arrays ARE in compact order, row by row
+            const T *srcs[4] = {d_rho, d_ux, d_uy, d_uz};
+            void *dsts[4] = {rho, ux, uy, uz};
+            const size_t rows = (size_t)d.ny * (size_t)(own_z1 - own_z0);
+            for (int k = 0; k < 4; k++)
+                if (dsts[k])
+                    CK(cudaMemcpy2DAsync(dsts[k], (size_t)d.nx * sizeof(T), srcs[k] + plane_c(own_z0), (size_t)box.px * sizeof(T),
+                                         (size_t)d.nx * sizeof(T), rows, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (first) *first = compact_first;
+            if (count) *count = stored_own;
+            return 0;
+        }
+        // dense storage: gather into compact order one group of planes at a time through two small
+        // persistent staging buffers -- the gather of group g+1 runs while group g crosses PCIe on a
+        // second stream
+        const long long group_cells = 16LL << 20;
         const int gplanes = (int)std::max<long long>(1, group_cells / box.plane);
         long long maxn = 1;
         for (int z = own_z0; z < own_z1; z += gplanes) {
             const int zb = std::min(own_z1, z + gplanes);
             maxn = std::max(maxn, plane_first[(size_t)(zb - box.z0)] - plane_first[(size_t)(z - box.z0)]);
         }
-        if ((size_t)maxn * 4 > stage_elems) {
+        if ((size_t)maxn * 8 > stage_elems) {
             if (d_stage) cudaFree(d_stage), d_stage = nullptr;
-            stage_elems = (size_t)maxn * 4;
+            stage_elems = (size_t)maxn * 8;
             CK(cudaMalloc((void **)&d_stage, stage_elems * sizeof(T)));
         }
+        if (!st_copy) {
+            CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++) {
+                CK(cudaEventCreateWithFlags(&ev_gathered[k], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ev_copied[k], cudaEventDisableTiming));
+            }
+        }
         char *outs[4] = {(char *)rho, (char *)ux, (char *)uy, (char *)uz};
+        int g = 0;
         for (int z = own_z0; z < own_z1; z += gplanes) {
             const int zb = std::min(own_z1, z + gplanes);
             const long long f0 = plane_first[(size_t)(z - box.z0)], cnt = plane_first[(size_t)(zb - box.z0)] - f0;
             if (cnt <= 0) continue;
-            CK(launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, z, zb, fluid_label, f0, d_stage,
-                                       d_stage + maxn, d_stage + 2 * maxn, d_stage + 3 * maxn, st));
+            T *buf = d_stage + (size_t)(g & 1) * 4 * maxn;
+            if (g >= 2) CK(cudaStreamWaitEvent(st, ev_copied[g & 1], 0));  // the copy out of this half is done
+            CK(launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, z, zb, fluid_label, f0, buf, buf + maxn,
+                                       buf + 2 * maxn, buf + 3 * maxn, st));
             launches++;
+            CK(cudaEventRecord(ev_gathered[g & 1], st));
+            CK(cudaStreamWaitEvent(st_copy, ev_gathered[g & 1], 0));
             for (int k = 0; k < 4; k++)
                 if (outs[k])
-                    CK(cudaMemcpyAsync(outs[k] + (size_t)(f0 - compact_first) * sizeof(T), d_stage + (size_t)k * maxn,
-                                       (size_t)cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(outs[k] + (size_t)(f0 - compact_first) * sizeof(T), buf + (size_t)k * maxn,
+                                       (size_t)cnt * sizeof(T), cudaMemcpyDeviceToHost, st_copy));
+            CK(cudaEventRecord(ev_copied[g & 1], st_copy));
+            g++;
         }
+        CK(cudaStreamSynchronize(st_copy));
         CK(cudaStreamSynchronize(st));
         if (first) *first = compact_first;
         if (count) *count = stored_own;
@@ -1133,6 +1321,25 @@ struct Solver final : SolverBase {
         int r = fetch_for_output();
         if (r) return r;
         if (out_format == LBM_OUT_BINARY_VTK) return output_save_binary(t);
+        return write_ascii(t);
+    }
+    // ONE byte-compatible ASCII file for a run sharded over several slabs: the group gathers the
+    // index table (Cartesian, whole box) and the fields (compact order, NLATTICE entries) and any slab
+    // handle formats them -- same code as the single-domain writer
+    int write_global(int t, const int32_t *index_global, const void *rho, const void *ux, const void *uy, const void *uz,
+                     int64_t nlattice) override {
+        std::vector<int32_t> si;
+        std::vector<T> sr, sx, sy, sz;
+        si.swap(w_index), sr.swap(w_rho), sx.swap(w_ux), sy.swap(w_uy), sz.swap(w_uz);
+        w_index.assign(index_global, index_global + (size_t)d.nx * d.ny * d.nz);
+        const size_t n = (size_t)nlattice;
+        w_rho.assign((const T *)rho, (const T *)rho + n), w_ux.assign((const T *)ux, (const T *)ux + n);
+        w_uy.assign((const T *)uy, (const T *)uy + n), w_uz.assign((const T *)uz, (const T *)uz + n);
+        int r = write_ascii(t);
+        si.swap(w_index), sr.swap(w_rho), sx.swap(w_ux), sy.swap(w_uy), sz.swap(w_uz);
+        return r;
+    }
+    int write_ascii(int t) {
         const int NX = d.nx, NY = d.ny, NZ = d.nz;
         const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
         const float C_pre = C_rho * C_U * C_U;
@@ -1201,6 +1408,29 @@ struct Solver final : SolverBase {
         ofs << "VECTORS VELOCITY float\n";
         format_planes(2, parts), flush();
         ofs.close();
+        return 0;
+    }
+
+    // write_once(): cor.cu:1033-1051 -- "x,y,z,ux,uy,uz" of every inlet / outlet node (labels 2,3,5,6,7), %f.
+    // (coronary.cu defines it but never calls it; the reference's h_u* of those nodes are whatever the
+    // device buffers held, here they are 0: nothing ever writes moments of non-fluid nodes.)
+    int write_bc_csv(const char *path) override {
+        if (lo_halo || hi_halo) FAIL(LBM_ERR_STATE, "lbm_write_bc_csv needs a single-domain handle");
+        int r = fetch_for_output();
+        if (r) return r;
+        std::vector<int32_t> geo((size_t)d.nx * d.ny * d.nz);
+        if ((r = get_geo(geo.data()))) return r;
+        FILE *f = fopen(path, "w+");
+        if (!f) FAIL(LBM_ERR_IO, "cannot write '%s'", path);
+        for (int z = 0; z < d.nz; z++)
+            for (int y = 0; y < d.ny; y++)
+                for (int x = 0; x < d.nx; x++) {
+                    const size_t c = (size_t)x + (size_t)d.nx * ((size_t)y + (size_t)d.ny * z);
+                    const int type = geo[c], i = w_index[c];
+                    if ((type == 2 || type == 3 || type == 5 || type == 6 || type == 7) && i >= 0)
+                        fprintf(f, "%d,%d,%d,%f,%f,%f\n", x, y, z, (double)(float)w_ux[i], (double)(float)w_uy[i], (double)(float)w_uz[i]);
+                }
+        fclose(f);
         return 0;
     }
 
@@ -1564,5 +1794,356 @@ int lbm_step_end(lbm_handle h) { H_OR_FAIL; return h->s->step_end(); }
 int lbm_last_velsum(lbm_handle h, double *v) { H_OR_FAIL; return v ? h->s->last_velsum(v) : LBM_ERR_ARG; }
 void *lbm_stream(lbm_handle h) { return h ? h->s->stream_ptr() : nullptr; }
 int lbm_sync(lbm_handle h) { H_OR_FAIL; return h->s->sync(); }
+int lbm_slab_step(lbm_handle h, int32_t n, int32_t flags_last, double *S_out, float *elapsed_ms) {
+    H_OR_FAIL;
+    return h->s->slab_steps(n, flags_last, S_out, elapsed_ms);
+}
+int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset) {
+    H_OR_FAIL;
+    return h->s->sync_export(handle, ptr, byte_offset);
+}
+int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync) { H_OR_FAIL; return h->s->sync_attach(side, peer_sync); }
+int lbm_write_bc_csv(lbm_handle h, const char *path) { H_OR_FAIL; return path ? h->s->write_bc_csv(path) : LBM_ERR_ARG; }
+
+// ============================================================================
+// several z-slabs driven from ONE process (lbm_create_distributed)
+// ============================================================================
+struct lbm_group_s {
+    lbm_case_desc d;
+    std::vector<lbm_handle> h;
+    std::vector<int> dev;
+    std::string err;
+    int64_t nlattice = 0;
+    bool ready = false;
+    int fail(int code, const std::string &m) {
+        err = m;
+        return code;
+    }
+    int from(int r, int code) {  // propagate a slab's error
+        if (code) err = lbm::fmt("slab %d: %s", r, lbm_last_error(h[(size_t)r]));
+        return code;
+    }
+};
+static thread_local std::string g_group_error;
+#define G_OR_FAIL \
+    if (!g) return LBM_ERR_ARG
+
+int lbm_create_distributed(const lbm_case_desc *desc, int32_t nslabs, const int32_t *devices, lbm_group *out) {
+    if (!desc || !out || nslabs < 1 || nslabs > desc->nz) {
+        g_group_error = "lbm_create_distributed: bad arguments (1 <= nslabs <= nz)";
+        return LBM_ERR_ARG;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_group_error = "no usable CUDA device: liblbm_b200 has no CPU path";
+        return LBM_ERR_NO_DEVICE;
+    }
+    auto *g = new lbm_group_s();
+    g->d = *desc;
+    const int base = desc->nz / nslabs, rem = desc->nz % nslabs;  // contiguous, near-equal z ranges
+    int z = 0;
+    for (int r = 0; r < nslabs; r++) {
+        lbm_case_desc dr = *desc;
+        const int n = base + (r < rem ? 1 : 0);
+        dr.z_begin = z, dr.z_end = z + n, z += n;
+        dr.device = devices ? devices[r] : r % ndev;
+        lbm_handle hr = nullptr;
+        int rc = lbm_create(&dr, &hr);
+        if (rc) {
+            g_group_error = lbm::fmt("slab %d: %s", r, lbm_last_error(nullptr));
+            for (auto x : g->h) lbm_destroy(x);
+            delete g;
+            return rc;
+        }
+        g->h.push_back(hr), g->dev.push_back(dr.device);
+    }
+    *out = g;
+    return LBM_OK;
+}
+int lbm_group_destroy(lbm_group g) {
+    G_OR_FAIL;
+    for (auto x : g->h) lbm_sync(x);
+    for (auto x : g->h) lbm_destroy(x);
+    delete g;
+    return LBM_OK;
+}
+const char *lbm_group_last_error(lbm_group g) { return g ? g->err.c_str() : g_group_error.c_str(); }
+int32_t lbm_group_size(lbm_group g) { return g ? (int32_t)g->h.size() : -1; }
+lbm_handle lbm_group_slab(lbm_group g, int32_t r) { return g && r >= 0 && r < (int)g->h.size() ? g->h[(size_t)r] : nullptr; }
+
+// geo_pre .. initialize on every slab, compact numbering continued across slabs (bif:241-252), then the
+// slabs are wired to each other: peer stores for the crossing populations, events for the ordering
+int lbm_group_setup(lbm_group g, const int32_t *flag_cartesian, const float *inlet_uy, const float *outlet_uy,
+                    int64_t *nlattice) {
+    G_OR_FAIL;
+    const int P = (int)g->h.size();
+    int rc;
+    for (int r = 0; r < P; r++) {
+        if (flag_cartesian && (rc = g->from(r, lbm_set_flag(g->h[(size_t)r], flag_cartesian)))) return rc;
+        if ((rc = g->from(r, lbm_geo_pre(g->h[(size_t)r])))) return rc;
+    }
+    std::vector<int64_t> cnt((size_t)P), off((size_t)P);
+    int64_t total = 0;
+    for (int r = 0; r < P; r++) {
+        if ((rc = g->from(r, lbm_local_stored_count(g->h[(size_t)r], &cnt[(size_t)r])))) return rc;
+        off[(size_t)r] = total, total += cnt[(size_t)r];
+    }
+    const bool want_planes = g->d.case_rule == LBM_CASE_GEO_Y_INOUT;
+    for (int r = 0; r < P; r++) {
+        lbm_handle h = g->h[(size_t)r];
+        if ((rc = g->from(r, lbm_set_compact_offset(h, off[(size_t)r], total)))) return rc;
+        if ((rc = g->from(r, lbm_index_transform(h, nullptr)))) return rc;
+        if (want_planes) {
+            if (inlet_uy && outlet_uy) rc = lbm_set_bc_planes(h, inlet_uy, outlet_uy);
+            else rc = lbm_read_vel(h);  // bif:255-327
+            if ((rc = g->from(r, rc))) return rc;
+        }
+        if ((rc = g->from(r, lbm_initialize(h)))) return rc;
+    }
+    // wiring
+    for (int r = 0; r + 1 < P; r++) {
+        const int da = g->dev[(size_t)r], db = g->dev[(size_t)r + 1];
+        if (da != db) {
+            int ok_ab = 0, ok_ba = 0;
+            cudaDeviceCanAccessPeer(&ok_ab, da, db), cudaDeviceCanAccessPeer(&ok_ba, db, da);
+            if (!ok_ab || !ok_ba) return g->fail(LBM_ERR_CUDA, lbm::fmt("devices %d and %d cannot access each other's memory", da, db));
+            cudaSetDevice(da);
+            cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return g->fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+            cudaSetDevice(db);
+            e = cudaDeviceEnablePeerAccess(da, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return g->fail(LBM_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    struct Exp {
+        void *ptrs[2];
+        int64_t qs, halo[2], face[2];
+    };
+    std::vector<Exp> ex((size_t)P);
+    for (int r = 0; r < P; r++)
+        if ((rc = g->from(r, lbm_p2p_export(g->h[(size_t)r], nullptr, ex[(size_t)r].ptrs, nullptr, &ex[(size_t)r].qs, ex[(size_t)r].halo,
+                                            ex[(size_t)r].face))))
+            return rc;
+    for (int r = 0; r < P; r++)
+        for (int side = 0; side < 2; side++) {
+            const int nb = side == 0 ? r - 1 : r + 1;
+            if (nb < 0 || nb >= P) continue;
+            const Exp &e = ex[(size_t)nb];
+            // my low face feeds the neighbour's HIGH halo plane and vice versa
+            if ((rc = g->from(r, lbm_p2p_attach(g->h[(size_t)r], side, e.ptrs[0], e.ptrs[1], e.qs, e.halo[1 - side], e.face[1 - side]))))
+                return rc;
+            g->h[(size_t)r]->s->set_inproc_neighbour(side, g->h[(size_t)nb]->s);
+        }
+    g->nlattice = total, g->ready = true;
+    if (nlattice) *nlattice = total;
+    return LBM_OK;
+}
+
+// one time step on every slab: launches only; slab r+1 is enqueued right after slab r so that no stream
+// runs ahead of its neighbours by more than the launch queue allows
+static int group_enqueue(lbm_group g, int flags, int slot) {
+    for (size_t r = 0; r < g->h.size(); r++) {
+        SolverBase *s = g->h[r]->s;
+        int rc = s->enqueue_step(flags, slot >= 0 ? s->acc_slot(slot) : s->acc_slot(0));
+        if (rc) return g->from((int)r, rc);
+    }
+    return 0;
+}
+static int group_sync(lbm_group g) {
+    for (size_t r = 0; r < g->h.size(); r++) {
+        int rc = lbm_sync(g->h[r]);
+        if (rc) return g->from((int)r, rc);
+    }
+    return 0;
+}
+int lbm_group_step(lbm_group g, int32_t n, float *elapsed_ms) {
+    G_OR_FAIL;
+    if (!g->ready) return g->fail(LBM_ERR_STATE, "lbm_group_step before lbm_group_setup");
+    if (n < 0) return g->fail(LBM_ERR_ARG, "negative step count");
+    int rc = group_sync(g);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++)
+        if ((rc = group_enqueue(g, i == n - 1 ? LBM_STEP_MOMENTS : 0, -1))) return rc;
+    if ((rc = group_sync(g))) return rc;
+    if (elapsed_ms) *elapsed_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return LBM_OK;
+}
+int64_t lbm_group_num_fluid(lbm_group g) {
+    if (!g) return -1;
+    int64_t n = 0;
+    for (auto x : g->h) n += lbm_num_fluid(x);
+    return n;
+}
+// "all-reduced" reductions: the sum of the slabs' shares
+int lbm_group_residual(lbm_group g, int32_t kind, double *value) {
+    G_OR_FAIL;
+    if (!value) return LBM_ERR_ARG;
+    double acc = 0.0;
+    for (size_t r = 0; r < g->h.size(); r++) {
+        double v = 0.0;
+        int rc = lbm_residual(g->h[r], kind, &v);
+        if (rc) return g->from((int)r, rc);
+        acc += v;
+    }
+    *value = acc;
+    return LBM_OK;
+}
+// fields of the whole domain in the reference's compact order (NLATTICE entries each)
+int lbm_group_get_fields(lbm_group g, void *rho, void *ux, void *uy, void *uz) {
+    G_OR_FAIL;
+    if (!g->ready) return g->fail(LBM_ERR_STATE, "lbm_group_get_fields before lbm_group_setup");
+    const size_t es = g->d.precision == LBM_F64 ? 8 : 4;
+    int64_t first = 0;
+    for (size_t r = 0; r < g->h.size(); r++) {
+        int64_t cnt = 0;
+        if ((lbm_local_stored_count(g->h[r], &cnt))) return g->from((int)r, LBM_ERR_STATE);
+        auto at = [&](void *p) { return p ? (void *)((char *)p + (size_t)first * es) : nullptr; };
+        int rc = lbm_get_fields(g->h[r], at(rho), at(ux), at(uy), at(uz), nullptr, nullptr);
+        if (rc) return g->from((int)r, rc);
+        first += cnt;
+    }
+    return LBM_OK;
+}
+int lbm_group_get_index(lbm_group g, int32_t *index_cartesian) {
+    G_OR_FAIL;
+    size_t at = 0;
+    for (size_t r = 0; r < g->h.size(); r++) {
+        int rc = lbm_get_index(g->h[r], index_cartesian + at);
+        if (rc) return g->from((int)r, rc);
+        at += (size_t)g->d.nx * g->d.ny * (size_t)(g->h[r]->s->d.z_end - g->h[r]->s->d.z_begin);
+    }
+    return LBM_OK;
+}
+int lbm_group_set_output_format(lbm_group g, int32_t format) {
+    G_OR_FAIL;
+    for (size_t r = 0; r < g->h.size(); r++) {
+        int rc = lbm_set_output_format(g->h[r], format);
+        if (rc) return g->from((int)r, rc);
+    }
+    return LBM_OK;
+}
+// outputSave(t) for a sharded run: ASCII -> ONE file, byte-compatible with the single-domain writer (the
+// slabs' fields are gathered on the host); binary -> every slab writes its own piece
+int lbm_group_output_save(lbm_group g, int32_t t) {
+    G_OR_FAIL;
+    if (!g->ready) return g->fail(LBM_ERR_STATE, "lbm_group_output_save before lbm_group_setup");
+    if (g->h[0]->s->out_format == LBM_OUT_BINARY_VTK) {
+        for (size_t r = 0; r < g->h.size(); r++) {
+            int rc = lbm_output_save(g->h[r], t);
+            if (rc) return g->from((int)r, rc);
+        }
+        return LBM_OK;
+    }
+    const size_t es = g->d.precision == LBM_F64 ? 8 : 4, n = (size_t)g->nlattice;
+    std::vector<int32_t> idx((size_t)g->d.nx * g->d.ny * g->d.nz);
+    std::vector<char> f(4 * n * es);
+    int rc = lbm_group_get_index(g, idx.data());
+    if (rc) return rc;
+    if ((rc = lbm_group_get_fields(g, f.data(), f.data() + n * es, f.data() + 2 * n * es, f.data() + 3 * n * es))) return rc;
+    return g->from(0, g->h[0]->s->write_global(t, idx.data(), f.data(), f.data() + n * es, f.data() + 2 * n * es,
+                                                f.data() + 3 * n * es, g->nlattice));
+}
+
+// ldc.cu:653-685 / pos.cu:986-1019 on several slabs: S_k = sum over slabs of each slab's share, the
+// stopping rule applied on the host exactly as in the single-domain loop (Solver::run_converge)
+int lbm_group_run_converge(lbm_group g, int32_t max_it, double tol_d, int32_t stag_max, int32_t time_save, int32_t write_files,
+                           int32_t *iterations, double *residual_out) {
+    G_OR_FAIL;
+    if (!g->ready) return g->fail(LBM_ERR_STATE, "run before lbm_group_setup");
+    if (time_save <= 0) return g->fail(LBM_ERR_ARG, "time_save must be positive");
+    const int P = (int)g->h.size();
+    std::ofstream logfile;
+    if (write_files) logfile.open(std::string(g->d.out_dir) + "/CONVERGENCE.log");
+    const auto t0 = std::chrono::steady_clock::now();
+    const float tol = (float)tol_d;
+    float residual = 0.f, sum_current = 0.f;
+    int k = 0, tol_count = 0, rc;
+    const int max_batch = 48;
+    std::vector<double> S((size_t)max_batch), part((size_t)max_batch);
+    while (k <= max_it && tol_count <= stag_max) {
+        int nb = std::min(max_batch, std::max(1, stag_max + 1 - tol_count));
+        nb = std::min(nb, max_it - k + 1);
+        for (int j = 0; j < nb; j++)
+            if ((k + j) % time_save == 0) {
+                nb = j + 1;
+                break;
+            }
+        for (int r = 0; r < P; r++)
+            if ((rc = g->from(r, g->h[(size_t)r]->s->zero_acc(0, nb)))) return rc;
+        for (int j = 0; j < nb; j++)
+            if ((rc = group_enqueue(g, LBM_STEP_MOMENTS | LBM_STEP_VELSUM, j))) return rc;
+        std::fill(S.begin(), S.end(), 0.0);
+        for (int r = 0; r < P; r++) {
+            if ((rc = g->from(r, g->h[(size_t)r]->s->fetch_acc(0, nb, part.data())))) return rc;
+            for (int j = 0; j < nb; j++) S[(size_t)j] += part[(size_t)j];
+        }
+        for (int j = 0; j < nb; j++) {
+            const float sum_next = (float)S[(size_t)j];
+            residual = std::fabs(sum_next - sum_current) / sum_next;
+            if (k % time_save == 0 && write_files) {
+                const float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                std::cout << "ITERATION # " << k << ", collapse time: " << milli << " ms, residual:" << residual << std::endl;
+                logfile << residual << std::endl;
+                if ((rc = lbm_group_output_save(g, k))) return rc;
+            }
+            k++;
+            sum_current = sum_next;
+            if (residual <= tol) tol_count++;
+            if (!(k <= max_it && tol_count <= stag_max)) break;
+        }
+    }
+    const float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (write_files) {
+        if ((rc = lbm_group_output_save(g, k))) return rc;
+        std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << g->nlattice << std::endl;
+        std::cout << "Residual is " << residual << std::endl;
+        logfile << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << g->nlattice << " ERROR IS" << residual
+                << std::endl;
+    }
+    if (iterations) *iterations = k;
+    if (residual_out) *residual_out = residual;
+    return LBM_OK;
+}
+// bif.cu:1246-1274 / cor.cu:1100-1132 on several slabs; the residual between saves is the device reduction
+// sum(u^2) over the slabs (the single-domain loop sums the same terms on the host in long double)
+int lbm_group_run_fixed(lbm_group g, int32_t repeat, int32_t time_save, int32_t write_files) {
+    G_OR_FAIL;
+    if (!g->ready) return g->fail(LBM_ERR_STATE, "run before lbm_group_setup");
+    if (time_save <= 0) return g->fail(LBM_ERR_ARG, "time_save must be positive");
+    std::ofstream logfile;
+    if (write_files) logfile.open(std::string(g->d.out_dir) + "/CONVERGENCE.log");
+    const auto t0 = std::chrono::steady_clock::now();
+    float residual = 0.f;
+    int done = 0, rc;
+    double sum1 = 0.0, sum2 = 0.0;
+    while (done <= repeat) {
+        const int i_save = ((done + time_save - 1) / time_save) * time_save;
+        const int upto = std::min(i_save, repeat);
+        if ((rc = lbm_group_step(g, upto - done + 1, nullptr))) return rc;
+        done = upto + 1;
+        if (upto % time_save == 0) {
+            sum1 = sum2;  // fields of the previous save (0 at first)
+            if ((rc = lbm_group_residual(g, LBM_RES_U2SUM, &sum2))) return rc;
+            residual = (float)(std::fabs(sum1 - sum2) / sum2);
+            const float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (write_files) {
+                logfile << residual << std::endl;
+                std::cout << "ITERATION # " << upto << ", collapse time: " << milli << " ms, residual:" << residual << std::endl;
+                if ((rc = lbm_group_output_save(g, upto))) return rc;
+            }
+        }
+    }
+    const float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (write_files) {
+        std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << g->nlattice << std::endl;
+        logfile << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << g->nlattice << " ERROR IS" << residual
+                << std::endl;
+    }
+    return LBM_OK;
+}
 
 }  // extern "C"

@@ -764,6 +764,57 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
     return cudaGetLastError();
 }
 
+// ---- neighbour handshake between z-slabs that live in different processes (one process per GPU)
+// A slab may start the face launches of step t+1 only after both neighbours finished the face launches of
+// step t (they read the halo plane this slab is about to overwrite, and wrote the one it is about to read).
+// Each slab owns a small sync block in its own device memory: [0] steps finished by the LOW neighbour,
+// [1] by the HIGH neighbour -- written remotely by that neighbour (peer memory over NVLink), polled locally
+// -- [2] is set when a wait gave up.  Two single-thread kernels per step; the waiting one sleeps between
+// polls and gives up after `timeout_ns` instead of hanging the device when a neighbour died.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_slab_wait(unsigned long long *sync, unsigned long long need_lo, unsigned long long need_hi,
+                            unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_ns();
+    for (int side = 0; side < 2; side++) {
+        const unsigned long long need = side ? need_hi : need_lo;
+        if (need == 0) continue;
+        while (ld_acquire_sys(sync + side) < need) {
+            if (global_ns() - t0 > timeout_ns) {
+                sync[2] = 1ull;
+                return;
+            }
+            __nanosleep(100);
+        }
+    }
+}
+__global__ void k_slab_signal(unsigned long long *peer_lo, unsigned long long *peer_hi, unsigned long long value) {
+    __threadfence_system();  // the face launches before this kernel are complete; order this thread's store after them
+    if (peer_lo) st_release_sys(peer_lo, value);
+    if (peer_hi) st_release_sys(peer_hi, value);
+}
+cudaError_t launch_slab_wait(unsigned long long *sync, unsigned long long need_lo, unsigned long long need_hi,
+                             unsigned long long timeout_ns, cudaStream_t s) {
+    k_slab_wait<<<1, 1, 0, s>>>(sync, need_lo, need_hi, timeout_ns);
+    return cudaGetLastError();
+}
+cudaError_t launch_slab_signal(unsigned long long *peer_lo, unsigned long long *peer_hi, unsigned long long value,
+                               cudaStream_t s) {
+    k_slab_signal<<<1, 1, 0, s>>>(peer_lo, peer_hi, value);
+    return cudaGetLastError();
+}
+
 // ---- sparse storage
 cudaError_t launch_build_segments(const uint32_t *nodec, const long long *cart, const int32_t *index, Box box,
                                   int own_zl0, long long id0, long long id1, long long id_first, int32_t *counts,

@@ -138,6 +138,12 @@ template <typename T>
 cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box box, int zl, int side,
                                const T *buf, cudaStream_t s);
 
+// neighbour handshake of z-slabs in different processes (flags in peer memory), lbm_geo.cu
+cudaError_t launch_slab_wait(unsigned long long *sync, unsigned long long need_lo, unsigned long long need_hi,
+                             unsigned long long timeout_ns, cudaStream_t s);
+cudaError_t launch_slab_signal(unsigned long long *peer_lo, unsigned long long *peer_hi, unsigned long long value,
+                               cudaStream_t s);
+
 // ---- sparse storage (reference compact order + run segments), lbm_geo.cu
 constexpr int SEG_REC = 48;   // int32 per segment record: two pieces of 24, see k_seg_build
 constexpr int SEG_HALF = 24;

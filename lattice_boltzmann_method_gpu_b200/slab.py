@@ -8,6 +8,11 @@ owned plane -- one contiguous staging buffer per face, packed by the library rig
 planes were computed so the transfer overlaps the interior update -- with
 torch.distributed P2P ops (NCCL over NVLink on GPUs; gloo on CPU for the host-logic tests).
 
+With the fused peer-store exchange (the default) the time loop itself is `lbm_slab_step` inside the
+library: neighbours are ordered by progress flags in peer memory, so neither Python nor NCCL runs per
+step; torch.distributed only bootstraps (counts, IPC handles) and all-reduces the residual when the
+caller asks for one.
+
 Nothing here computes: the kernels live in liblbm_b200.so.  `exchange_halos` and `slab_ranges` /
 `compact_offsets` are backend-agnostic so the same code runs under gloo in the CPU tests.
 """
@@ -83,7 +88,7 @@ class SlabCase(api.Case):
         self.world = dist.get_world_size(group)
         self._bufs = None
         self._p2p = False
-        self._tick = None
+        self._sync_ptrs = []
         self._mapped = []        # IPC handles this rank holds a mapping of
         self.p2p_error = None    # why enable_p2p fell back, if it did
 
@@ -109,29 +114,41 @@ class SlabCase(api.Case):
         self._wrap_buffers()
 
     def enable_p2p(self):
-        """Fused halo exchange: every rank maps its neighbours' population buffers (CUDA IPC over
-        NVLink) and the step kernel stores the crossing populations there itself; what is left of the
-        transport is one tiny all-reduce per step that keeps the slabs in lock-step."""
+        """Fused halo exchange: every rank maps its neighbours' population buffers and sync blocks (CUDA
+        IPC over NVLink); the step kernel stores the crossing populations there itself and the slabs
+        order their steps through progress flags in that memory (lbm_slab_step) -- no collective is
+        left in the time loop."""
         import torch
         import torch.distributed as dist
 
         mine = self.p2p_export()
         mine.pop("ptrs")  # raw pointers mean nothing in another process
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=self.group)
+        sy = self.sync_export()
+        # fixed-size record, one all_gather of bytes (no pickling): 3 IPC handles + 8 int64
+        rec = np.zeros(3 * 64 + 8 * 8, dtype=np.uint8)
+        rec[0:64] = np.frombuffer(mine["handles"][0], dtype=np.uint8)
+        rec[64:128] = np.frombuffer(mine["handles"][1], dtype=np.uint8)
+        rec[128:192] = np.frombuffer(sy["handle"], dtype=np.uint8)
+        rec[192:].view(np.int64)[:] = [mine["boff"][0], mine["boff"][1], sy["boff"], mine["qs"], mine["halo_c0"][0],
+                                       mine["halo_c0"][1], mine["face_c0"][0], mine["face_c0"][1]]
+        t = torch.from_numpy(rec).cuda()
+        allt = torch.empty(self.world * rec.size, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allt, t, group=self.group)
+        allr = allt.cpu().numpy().reshape(self.world, rec.size)
         ok, attached = 1, []
         try:
             for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
                 if 0 <= nb < self.world:
+                    r = allr[nb]
+                    hs = [r[0:64].tobytes(), r[64:128].tobytes(), r[128:192].tobytes()]
+                    boff_a, boff_b, boff_s, qs, h0, h1, f0, f1 = (int(v) for v in r[192:].view(np.int64))
                     ptrs = []
-                    for h, o in zip(everyone[nb]["handles"], everyone[nb]["boff"]):
+                    for h, o in zip(hs, (boff_a, boff_b, boff_s)):
                         ptrs.append(api.p2p_open(h) + o)
                         self._mapped.append(h)
-                    pa, pb = ptrs
                     # my low face feeds the neighbour's HIGH halo plane and vice versa
-                    self.p2p_attach(side, pa, pb, everyone[nb]["qs"], everyone[nb]["halo_c0"][1 - side],
-                                    everyone[nb]["face_c0"][1 - side])
-                    attached.append(side)
+                    self.p2p_attach(side, ptrs[0], ptrs[1], qs, (h0, h1)[1 - side], (f0, f1)[1 - side])
+                    attached.append((side, ptrs[2]))
         except api.LbmError as e:
             ok, self.p2p_error = 0, str(e)
         # all ranks or none: a rank that cannot map its neighbour (no peer access / IPC) sends everyone
@@ -139,13 +156,28 @@ class SlabCase(api.Case):
         flag = torch.tensor([ok], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
-            for side in attached:
+            for side, _ in attached:
                 self.p2p_attach(side, None, None)
             self._release_mappings()
             return False
-        self._tick = torch.zeros(1, device="cuda")
+        self._sync_ptrs = attached
+        self._attach_sync()
         self._p2p = True
         return True
+
+    def _attach_sync(self):
+        """collective: every rank zeroes its progress counters, then nobody steps before all have"""
+        import torch.distributed as dist
+
+        dist.barrier(group=self.group)   # nobody is still stepping
+        for side, ptr in self._sync_ptrs:
+            self.sync_attach(side, ptr)
+        dist.barrier(group=self.group)   # every counter is zero before the first new signal
+
+    def checkpoint_load(self, path):
+        super().checkpoint_load(path)
+        if self._p2p:
+            self._attach_sync()
 
     def _release_mappings(self):
         for h in self._mapped:
@@ -189,15 +221,6 @@ class SlabCase(api.Case):
     def _one_step(self, flags=0):
         import torch
 
-        if self._p2p:
-            import torch.distributed as dist
-
-            self.step_begin(flags)  # face planes first: their peer stores start crossing NVLink ...
-            self.step_interior()    # ... while the interior planes are updated
-            self.step_end()
-            with torch.cuda.stream(self._ext):  # in-stream barrier: nobody starts t+1 before all finished t
-                dist.all_reduce(self._tick, group=self.group)
-            return
         self.step_begin(flags)  # face planes + pack, queued on the library's stream
         (s_lo, r_lo), (s_hi, r_hi) = self._bufs
         # torch.distributed orders NCCL's stream after what `self._ext` holds so far (faces + pack)
@@ -210,13 +233,50 @@ class SlabCase(api.Case):
         self.step_end()  # unpack + buffer swap
 
     def step(self, n: int = 1):
+        if self._p2p:
+            self.slab_step(n)
+            return
         for i in range(int(n)):
             self._one_step(api.STEP_MOMENTS if i == n - 1 else 0)
         self.sync()
 
+    def run_converge(self, max_it=10000, tol=1e-6, stag_max=50, time_save=500, write_files=False):
+        """ldc.cu:653-685 on a sharded domain: S_k is all-reduced over the slabs once per batch of steps;
+        the stopping rule is the reference's, applied identically on every rank.  Returns (iterations,
+        residual).  File output of a multi-process run: lbm_set_output_format(BINARY) pieces per slab."""
+        import torch
+        import torch.distributed as dist
+
+        if not self._p2p:
+            raise api.LbmError(-2, "run_converge on slabs needs the fused exchange (enable_p2p)")
+        tol = np.float32(tol)
+        residual, s_cur, k, hits = np.float32(0), np.float32(0), 0, 0
+        while k <= max_it and hits <= stag_max:
+            nb = min(48, max(1, stag_max + 1 - hits), max_it - k + 1)
+            for j in range(nb):
+                if (k + j) % time_save == 0:
+                    nb = j + 1
+                    break
+            _, S = self.slab_step(nb, True, velsum=True)
+            t = torch.from_numpy(S).cuda()
+            dist.all_reduce(t, group=self.group)
+            for s_next in t.cpu().numpy().astype(np.float32):
+                residual = np.abs(s_next - s_cur) / s_next
+                if k % time_save == 0 and write_files:
+                    self.outputSave(k)
+                k += 1
+                s_cur = s_next
+                if residual <= tol:
+                    hits += 1
+                if not (k <= max_it and hits <= stag_max):
+                    break
+        return k, float(residual)
+
     def step_timed(self, n: int) -> float:
         import torch
 
+        if self._p2p:
+            return self.slab_step(n)[0]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(self._ext):
             e0.record()

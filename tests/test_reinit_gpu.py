@@ -74,7 +74,7 @@ def test_writer_follows_a_new_geometry(tmp_path):
     small, big = _tube_flag(40, 30, 40, 6.2), _tube_flag(40, 30, 40, 15.1)
     outs = []
     for first in (big, None):  # a handle that saw `big` before, and a fresh one
-        c = _bif_like(L.STORE_DENSE_AB, small, L, L.MATH_FAST)
+        c = _bif_like(L.STORE_DENSE_AB, small, L)
         d = tmp_path / ("a" if first is not None else "b")
         d.mkdir()
         c.close()

@@ -111,7 +111,7 @@ def run_variant(name, wd, inputs=()):
 
 def variants(outdir):
     """the patched-constant variants built by tools/make_reference_variants.py"""
-    sys.path.insert(0, str(ROOT / "tests"))
+    sys.path.insert(0, str(ROOT)), sys.path.insert(0, str(ROOT / "tests"))
     import helpers as H
 
     out = Path(outdir)
