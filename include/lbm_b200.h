@@ -63,7 +63,9 @@ typedef enum { LBM_F32 = 0, LBM_F64 = 1 } lbm_precision;
 typedef enum {
     LBM_STORE_DENSE_AB = 0,  /* box-dense SoA, two buffers, fused pull step            */
     LBM_STORE_DENSE_AA = 1,  /* box-dense SoA, ONE buffer, in-place AA-pattern streaming */
-    LBM_STORE_SPARSE_AB = 2  /* reference compact order (NLATTICE entries), run-segment indirect addressing, two buffers */
+    LBM_STORE_SPARSE_AB = 2, /* reference compact order (NLATTICE entries), run-segment indirect addressing, two buffers */
+    LBM_STORE_SPARSE_AA = 3  /* the same compact order, ONE buffer streamed in place; boundary links live in the fluid
+                                node's own slot, so solid nodes are never touched by a step */
 } lbm_storage;
 
 /* arithmetic of the fused kernel */
@@ -325,6 +327,13 @@ int lbm_group_output_save(lbm_group g, int32_t t); /* ASCII: ONE file, byte-iden
 int lbm_group_run_fixed(lbm_group g, int32_t repeat, int32_t time_save, int32_t write_files);
 int lbm_group_run_converge(lbm_group g, int32_t max_it, double tol, int32_t stag_max, int32_t time_save,
                            int32_t write_files, int32_t *iterations, double *residual);
+
+/* Self-checking build of the library (-DLBM_SELFCHECK; tools/selfcheck.py builds and runs it -- the stand-in for
+ * compute-sanitizer, which the GPU pool does not offer): out[0] = population accesses of the step kernels that
+ * fell outside the handle's buffers, out[1] = buffer elements touched by two different threads within one launch
+ * (the in-place storage relies on there being none), out[2] = step-kernel launches checked.  A normal build
+ * returns LBM_ERR_STATE. */
+int lbm_debug_selfcheck(lbm_handle h, uint64_t out[3]);
 
 /* write_once(): cor.cu:1033-1051 -- "x,y,z,ux,uy,uz" (%f) of every inlet / outlet node (labels 2,3,5,6,7) */
 int lbm_write_bc_csv(lbm_handle h, const char *path);

@@ -26,7 +26,7 @@ LIB_PATH = Path(os.environ["LBM_B200_LIB"]) if os.environ.get("LBM_B200_LIB") el
 # enums of include/lbm_b200.h
 CASE_LDC, CASE_POISEUILLE, CASE_GEO_Y_INOUT, CASE_GEO_OPENINGS = 0, 1, 2, 3
 F32, F64 = 0, 1
-STORE_DENSE_AB, STORE_DENSE_AA, STORE_SPARSE_AB = 0, 1, 2
+STORE_DENSE_AB, STORE_DENSE_AA, STORE_SPARSE_AB, STORE_SPARSE_AA = 0, 1, 2, 3
 MATH_FAST, MATH_STRICT = 0, 1
 BC_NONE, BC_V, BC_P, BC_VP = 0, 1, 2, 3
 SRC_CONST, SRC_PARABOLA, SRC_PLANE_INLET, SRC_PLANE_OUTLET = 0, 1, 2, 3
@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_voxelize_stl", "lbm_voxelize_triangles", "lbm_voxel_last_error", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
     "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
-    "lbm_slab_step", "lbm_sync_export", "lbm_sync_attach", "lbm_write_bc_csv",
+    "lbm_slab_step", "lbm_sync_export", "lbm_sync_attach", "lbm_write_bc_csv", "lbm_debug_selfcheck",
     "lbm_create_distributed", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size", "lbm_group_slab",
     "lbm_group_setup", "lbm_group_step", "lbm_group_num_fluid", "lbm_group_residual", "lbm_group_get_fields",
     "lbm_group_get_index", "lbm_group_set_output_format", "lbm_group_output_save", "lbm_group_run_fixed",
@@ -156,6 +156,7 @@ def load_library() -> C.CDLL:
         "lbm_sync_export": ([vp, vp, P(vp), P(i64)], C.c_int),
         "lbm_sync_attach": ([vp, i32, vp], C.c_int),
         "lbm_write_bc_csv": ([vp, C.c_char_p], C.c_int),
+        "lbm_debug_selfcheck": ([vp, vp], C.c_int),
         "lbm_create_distributed": ([P(CaseDesc), i32, vp, P(vp)], C.c_int),
         "lbm_group_destroy": ([vp], C.c_int),
         "lbm_group_last_error": ([vp], C.c_char_p),
@@ -345,6 +346,13 @@ class Case:
         self._ck(self._L.lbm_slab_step(self._h, int(n), STEP_MOMENTS if moments_last else 0,
                                        S.ctypes.data if velsum else None, C.byref(ms)))
         return ms.value, S
+
+    def selfcheck(self):
+        """(out-of-range accesses, elements touched by two threads in one launch, launches checked) of a
+        self-checking build; raises LbmError on a normal build"""
+        out = (C.c_uint64 * 3)()
+        self._ck(self._L.lbm_debug_selfcheck(self._h, out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def write_bc_csv(self, path):
         self._ck(self._L.lbm_write_bc_csv(self._h, os.fsencode(str(path))))

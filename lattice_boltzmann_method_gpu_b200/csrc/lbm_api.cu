@@ -85,6 +85,7 @@ struct SolverBase {
     virtual int halo_buffers(int side, void **send, void **recv, size_t *send_bytes, size_t *recv_bytes) = 0;
     virtual int sync() = 0;
     virtual void *stream_ptr() = 0;
+    virtual int selfcheck(uint64_t *out2) = 0;
     int64_t steps = 0, launches = 0, nfluid = 0, dev_bytes = 0;
 };
 
@@ -165,6 +166,11 @@ struct Solver final : SolverBase {
     int8_t *d_labelc = nullptr;
     int32_t *d_rec = nullptr, *d_chunk_cnt = nullptr;
     std::vector<long long> seg_plane_start;      // [owned planes + 1]
+    // in-place sparse storage: its own numbering (fluid nodes + single-cell x gaps), see lbm_geo.cu k_span_flags
+    int32_t *d_sid = nullptr;
+    uint2 *d_cmeta = nullptr;
+    std::vector<long long> sid_plane_first;      // [planes of the state box + 1] first own-numbering id of each plane
+    long long own_id0 = 0, own_id1 = 0;          // ids (storage numbering, local) of the owned planes
     long long halo_id0[2] = {0, 0}, halo_n[2] = {0, 0};   // compact range of the halo plane per side
     long long face_id0[2] = {0, 0}, face_n[2] = {0, 0};   // compact range of the outermost owned plane per side
 
@@ -176,8 +182,9 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
+        fr(d_sid), fr(d_cmeta);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
-        fr(d_sync);
+        fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto &e : ev_face)
@@ -222,6 +229,7 @@ struct Solver final : SolverBase {
         dfree(&d_fa), dfree(&d_fb), dfree(&d_rho), dfree(&d_ux), dfree(&d_uy), dfree(&d_uz);
         for (int sd = 0; sd < 2; sd++) dfree(&d_send[sd]), dfree(&d_recv[sd]);
         dfree(&d_cart), dfree(&d_nodec), dfree(&d_wallc), dfree(&d_labelc), dfree(&d_rec), dfree(&d_chunk_cnt);
+        dfree(&d_cmeta);
         dfree(&d_chunk_off), dfree(&d_plane_seg);
         if (d_stage) cudaFree(d_stage), d_stage = nullptr, stage_elems = 0;
         d_cur = d_nxt = nullptr;
@@ -485,7 +493,7 @@ struct Solver final : SolverBase {
     int initialize() override {
         if (!have_index) FAIL(LBM_ERR_STATE, "initialize before index_transform");
         CK(cudaSetDevice(d.device));
-        if (d.storage == LBM_STORE_SPARSE_AB) return initialize_sparse();
+        if (d.storage == LBM_STORE_SPARSE_AB || d.storage == LBM_STORE_SPARSE_AA) return initialize_sparse();
         if (d.storage != LBM_STORE_DENSE_AB && d.storage != LBM_STORE_DENSE_AA)
             FAIL(LBM_ERR_ARG, "unknown storage %d", d.storage);
         const bool aa = d.storage == LBM_STORE_DENSE_AA;
@@ -524,7 +532,7 @@ struct Solver final : SolverBase {
         ip.rho = d_rho, ip.ux = d_ux, ip.uy = d_uy, ip.uz = d_uz;
         ip.box = box, ip.case_rule = d.case_rule, ip.u_max = (T)d.u_max;
         for (int i = 0; i < LBM_MAX_BC; i++) ip.bc[i] = bc[i];
-        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out;
+        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out, ip.fluid_label = fluid_label;
         CK(launch_init<T>(ip, st));
         launches++;
         CK(cudaStreamSynchronize(st));
@@ -560,29 +568,64 @@ struct Solver final : SolverBase {
             int r = upload_planes();
             if (r) return r;
         }
-        const long long ns = stored_box;
+        const bool aa = d.storage == LBM_STORE_SPARSE_AA;
         const int nzl = box.z1 - box.z0, nown = own_z1 - own_z0;
+        const int zl_first = own_z0 - box.z0, zl_last = own_z1 - 1 - box.z0;
+        long long ns = stored_box;            // entries of the storage's arrays
+        const int32_t *numidx = d_index;      // cell -> id of the storage's numbering (+ num_first)
+        long long num_first = sp_first;
+        std::vector<long long> pfirst((size_t)nzl + 1);  // first local id of every plane of the state box
+        if (aa) {
+            // own numbering: fluid nodes and single-cell x gaps, z,y,x order (k_span_flags)
+            if (!d_sid && dalloc(&d_sid, (size_t)box.cells())) return LBM_ERR_NOMEM;
+            int32_t *keep = nullptr;
+            long long *d_pf = nullptr;
+            CK(cudaMalloc((void **)&keep, (size_t)box.cells() * sizeof(int32_t)));
+            cudaError_t ce = cudaMalloc((void **)&d_pf, (size_t)nzl * sizeof(long long));
+            if (ce == cudaSuccess) ce = launch_span_flags(d_label, box, fluid_label, keep, st);
+            if (ce == cudaSuccess)
+                ce = launch_compact(keep, d_sid, box.cells(), box.px, box.nx, 0, 0, d_scratch, scratch_ints, d_cnt + 7, box.plane, d_pf, st);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(pfirst.data(), d_pf, (size_t)nzl * sizeof(long long), cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(&ns, d_cnt + 7, sizeof ns, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            cudaFree(keep), cudaFree(d_pf);
+            CK(ce);
+            launches += 4;
+            pfirst[(size_t)nzl] = ns;
+            numidx = d_sid, num_first = 0;
+        } else {
+            for (int z = 0; z <= nzl; z++) pfirst[(size_t)z] = plane_first[(size_t)z] - sp_first;
+        }
+        sid_plane_first = pfirst;
         if (!d_cart) {
             if (dalloc(&d_cart, (size_t)ns) || dalloc(&d_nodec, (size_t)ns) || dalloc(&d_wallc, (size_t)ns) ||
                 dalloc(&d_labelc, (size_t)ns))
                 return LBM_ERR_NOMEM;
         }
-        CK(launch_compact_maps(d_index, d_node, d_wall, d_label, box.cells(), sp_first, d_cart, d_nodec, d_wallc, d_labelc, st));
+        if (aa) {  // gap cells are not fluid: they must read as "skip" whatever the cell's own node word says
+            CK(cudaMemsetAsync(d_nodec, 0xff, (size_t)ns * sizeof(uint32_t), st));
+        }
+        CK(launch_compact_maps(numidx, d_node, d_wall, d_label, box.cells(), num_first, d_cart, d_nodec, d_wallc, d_labelc, st));
         launches++;
-        // compact ranges of the halo planes and of the outermost owned planes
-        const int zl_first = own_z0 - box.z0, zl_last = own_z1 - 1 - box.z0;
-        halo_id0[0] = 0, halo_n[0] = lo_halo ? n_lo_stored : 0;
-        face_id0[0] = n_lo_stored, face_n[0] = lo_halo ? count_plane(zl_first) : 0;
-        halo_n[1] = hi_halo ? count_plane(nzl - 1) : 0, halo_id0[1] = ns - halo_n[1];
-        face_n[1] = hi_halo ? count_plane(zl_last) : 0, face_id0[1] = ns - halo_n[1] - face_n[1];
-        // segments: aligned 32-id chunks of the owned planes' compact range
-        const long long own_id0 = n_lo_stored, own_id1 = ns - halo_n[1];
+        // id ranges of the halo planes and of the outermost owned planes (a plane is one contiguous range)
+        auto plane_n = [&](int zl) { return pfirst[(size_t)zl + 1] - pfirst[(size_t)zl]; };
+        halo_id0[0] = 0, halo_n[0] = lo_halo ? plane_n(0) : 0;
+        face_id0[0] = pfirst[(size_t)zl_first], face_n[0] = lo_halo ? plane_n(zl_first) : 0;
+        halo_n[1] = hi_halo ? plane_n(nzl - 1) : 0, halo_id0[1] = ns - halo_n[1];
+        face_n[1] = hi_halo ? plane_n(zl_last) : 0, face_id0[1] = pfirst[(size_t)zl_last];
+        // segments: aligned 32-id chunks of the owned planes' id range
+        own_id0 = pfirst[(size_t)zl_first], own_id1 = pfirst[(size_t)zl_last + 1];
         const long long nchunks = (own_id1 - (own_id0 & ~31LL) + 31) / 32 + 1;
         if (!d_chunk_cnt && (dalloc(&d_chunk_cnt, (size_t)nchunks) || dalloc(&d_chunk_off, (size_t)nchunks) ||
                              dalloc(&d_plane_seg, (size_t)nown + 1)))
             return LBM_ERR_NOMEM;
-        CK(launch_build_segments(d_nodec, d_cart, d_index, box, zl_first, own_id0, own_id1, sp_first, d_chunk_cnt, d_chunk_off,
-                                 d_cnt + 5, nullptr, nullptr, st));
+        auto build = [&](int32_t *rec, long long *plane_seg) {
+            return aa ? launch_build_segments_rows(d_nodec, d_cart, d_sid, d_label, fluid_label, box, zl_first, own_id0, own_id1,
+                                                   d_chunk_cnt, d_chunk_off, d_cnt + 5, rec, plane_seg, st)
+                      : launch_build_segments(d_nodec, d_cart, d_index, box, zl_first, own_id0, own_id1, sp_first, d_chunk_cnt,
+                                              d_chunk_off, d_cnt + 5, rec, plane_seg, st);
+        };
+        CK(build(nullptr, nullptr));
         launches += 2;
         CK(cudaMemcpyAsync(&nseg, d_cnt + 5, sizeof nseg, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -591,8 +634,7 @@ struct Solver final : SolverBase {
         if (dalloc(&d_rec, (size_t)std::max<long long>(nseg, 1) * SEG_REC)) return LBM_ERR_NOMEM;
         CK(cudaMemsetAsync(d_rec, 0, (size_t)std::max<long long>(nseg, 1) * SEG_REC * sizeof(int32_t), st));
         CK(cudaMemsetAsync(d_plane_seg, 0x7f, ((size_t)nown + 1) * sizeof(long long), st));  // "no record yet"
-        CK(launch_build_segments(d_nodec, d_cart, d_index, box, zl_first, own_id0, own_id1, sp_first, d_chunk_cnt, d_chunk_off,
-                                 d_cnt + 5, d_rec, d_plane_seg, st));
+        CK(build(d_rec, d_plane_seg));
         launches++;
         {
             // first record of every owned plane (records are in plane order); planes without fluid take the next one's
@@ -603,10 +645,18 @@ struct Solver final : SolverBase {
             for (int z = nown - 1; z >= 0; z--)
                 if (seg_plane_start[(size_t)z] > nseg) seg_plane_start[(size_t)z] = seg_plane_start[(size_t)z + 1];
         }
+        if (aa) {
+            if (!d_cmeta && dalloc(&d_cmeta, (size_t)(ns / 32 + 2))) return LBM_ERR_NOMEM;
+            CK(launch_chunk_meta(d_nodec, ns, d_cmeta, st));
+            launches++;
+        }
         qstride = (ns + 64 + 31) & ~31LL;  // every direction's array starts 256-byte aligned
+        if (aa && qstride >= (1LL << 31) / 3) FAIL(LBM_ERR_ARG, "slab of %lld nodes is too large for 32-bit element offsets: use more z-slabs", ns);
         if (!d_fa) {
             const size_t fsize = (size_t)qstride * Q + 64;
-            if (dalloc(&d_fa, fsize) || dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
+            if (dalloc(&d_fa, fsize)) return LBM_ERR_NOMEM;
+            if (aa) d_fb = d_fa;  // one buffer, streamed in place
+            else if (dalloc(&d_fb, fsize)) return LBM_ERR_NOMEM;
             if (dalloc(&d_rho, (size_t)ns) || dalloc(&d_ux, (size_t)ns) || dalloc(&d_uy, (size_t)ns) || dalloc(&d_uz, (size_t)ns))
                 return LBM_ERR_NOMEM;
             for (int sd = 0; sd < 2; sd++) {
@@ -615,11 +665,11 @@ struct Solver final : SolverBase {
             }
         }
         InitParams<T> ip{};
-        ip.fa = d_fa, ip.fb = d_fb, ip.aa = 0, ip.qstride = qstride, ip.label = d_label;
+        ip.fa = d_fa, ip.fb = d_fb, ip.aa = aa ? 1 : 0, ip.qstride = qstride, ip.label = d_label;
         ip.rho = d_rho, ip.ux = d_ux, ip.uy = d_uy, ip.uz = d_uz;
         ip.box = box, ip.case_rule = d.case_rule, ip.u_max = (T)d.u_max;
         for (int i = 0; i < LBM_MAX_BC; i++) ip.bc[i] = bc[i];
-        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out;
+        ip.plane_in = d_plane_in, ip.plane_out = d_plane_out, ip.fluid_label = fluid_label;
         CK(launch_init_sparse<T>(ip, d_cart, ns, st));
         launches++;
         CK(cudaStreamSynchronize(st));
@@ -649,6 +699,13 @@ struct Solver final : SolverBase {
         p.parity = (int)(steps & 1);
         p.case_rule = d.case_rule;
         p.u_init = (T)d.u_max;
+#ifdef LBM_SELFCHECK
+        if (chk_prepare() == 0) {
+            p.chk_lo[0] = d_fa, p.chk_hi[0] = d_fa + chk_elems, p.chk_lo[1] = d_fb, p.chk_hi[1] = d_fb + chk_elems;
+            p.chk_shadow[0] = d_chk_shadow[0], p.chk_shadow[1] = d_fb == d_fa ? d_chk_shadow[0] : d_chk_shadow[1];
+            p.chk_count = d_chk_count, p.chk_launch = ++chk_launch_id;
+        }
+#endif
         // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
         static const char *const force = getenv("LBM_SPECULATIVE");  // tuning knob, read once
         p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
@@ -676,6 +733,16 @@ struct Solver final : SolverBase {
             }
             const long long zA = c0 / box.plane - (own_z0 - box.z0), zB = c1 / box.plane - (own_z0 - box.z0);
             sp.seg_begin = seg_plane_start[(size_t)zA], sp.seg_end = seg_plane_start[(size_t)zB];
+            if (d.storage == LBM_STORE_SPARSE_AA) {
+                sp.cartc = d_cart, sp.cmeta = d_cmeta;
+                sp.id_begin = sid_plane_first[(size_t)(c0 / box.plane)], sp.id_end = sid_plane_first[(size_t)(c1 / box.plane)];
+                sp.halo_lo_n = (int)halo_n[0], sp.halo_hi0 = (int)halo_id0[1];
+                if (sp.base.parity == 0 ? sp.id_end <= sp.id_begin : sp.seg_end <= sp.seg_begin) return 0;
+                if (d.math == LBM_MATH_STRICT) CK(launch_step_sparse_aa_strict<T>(sp, moments, resid, st));
+                else CK(launch_step_sparse_aa_fast<T>(sp, moments, resid, st));
+                launches++;
+                return 0;
+            }
             if (sp.seg_end <= sp.seg_begin) return 0;
             if (d.math == LBM_MATH_STRICT) CK(launch_step_sparse_strict<T>(sp, moments, resid, st));
             else CK(launch_step_sparse_fast<T>(sp, moments, resid, st));
@@ -804,7 +871,7 @@ struct Solver final : SolverBase {
         in_step = false;
         return 0;
     }
-    bool in_place() const { return d.storage == LBM_STORE_DENSE_AA; }
+    bool in_place() const { return d.storage == LBM_STORE_DENSE_AA || d.storage == LBM_STORE_SPARSE_AA; }
     int enqueue_step(int flags, double *acc) override {
         int r = step_begin_ex(flags, acc);
         if (r) return r;
@@ -1089,8 +1156,8 @@ struct Solver final : SolverBase {
         if (!have_moments) FAIL(LBM_ERR_STATE, "no moments yet: run lbm_step first");
         CK(cudaSetDevice(d.device));
         if (sparse)
-            CK(launch_reduce_fields_sparse<T>(d_ux, d_uy, d_uz, d_labelc, d_cart, box, n_lo_stored, n_lo_stored + stored_own,
-                                              kind, fluid_label, d.case_rule, d_acc + 1, st));
+            CK(launch_reduce_fields_sparse<T>(d_ux, d_uy, d_uz, d_labelc, d_cart, box, own_id0, own_id1, kind, fluid_label,
+                                              d.case_rule, d_acc + 1, st));
         else
             CK(launch_reduce_fields<T>(d_ux, d_uy, d_uz, d_label, box, own_z0, own_z1, kind, fluid_label, d.case_rule,
                                        d_acc + 1, st));
@@ -1121,7 +1188,7 @@ struct Solver final : SolverBase {
         if (!have_init) FAIL(LBM_ERR_STATE, "get_fields before initialize");
         CK(cudaSetDevice(d.device));
         const size_t n = (size_t)stored_own;
-        if (sparse) {  // the device arrays already are in compact order
+        if (sparse && d.storage != LBM_STORE_SPARSE_AA) {  // the device arrays already are in compact order
             const T *srcs[4] = {d_rho, d_ux, d_uy, d_uz};
             void *dsts[4] = {rho, ux, uy, uz};
             for (int k = 0; k < 4; k++)
@@ -1131,7 +1198,7 @@ struct Solver final : SolverBase {
             if (count) *count = stored_own;
             return 0;
         }
-        if (store_all()) {
+        if (store_all() && !sparse) {
             // every node of the box is stored (ldc.cu:54): the moment arrays ARE in compact order, row by row
             const T *srcs[4] = {d_rho, d_ux, d_uy, d_uz};
             void *dsts[4] = {rho, ux, uy, uz};
@@ -1175,8 +1242,8 @@ struct Solver final : SolverBase {
             if (cnt <= 0) continue;
             T *buf = d_stage + (size_t)(g & 1) * 4 * maxn;
             if (g >= 2) CK(cudaStreamWaitEvent(st, ev_copied[g & 1], 0));  // the copy out of this half is done
-            CK(launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, box, z, zb, fluid_label, f0, buf, buf + maxn,
-                                       buf + 2 * maxn, buf + 3 * maxn, st));
+            CK(launch_gather_fields<T>(d_rho, d_ux, d_uy, d_uz, d_label, d_index, sparse ? d_sid : nullptr, box, z, zb, fluid_label,
+                                       f0, buf, buf + maxn, buf + 2 * maxn, buf + 3 * maxn, st));
             launches++;
             CK(cudaEventRecord(ev_gathered[g & 1], st));
             CK(cudaStreamWaitEvent(st_copy, ev_gathered[g & 1], 0));
@@ -1197,6 +1264,20 @@ struct Solver final : SolverBase {
         if (!have_init) FAIL(LBM_ERR_STATE, "get_populations before initialize");
         CK(cudaSetDevice(d.device));
         const size_t n = (size_t)stored_own;
+        if (d.storage == LBM_STORE_SPARSE_AA) {
+            T *tmp = nullptr;
+            CK(cudaMalloc((void **)&tmp, std::max<size_t>(n, 1) * Q * sizeof(T)));
+            cudaError_t e = cudaMemsetAsync(tmp, 0, std::max<size_t>(n, 1) * Q * sizeof(T), st);
+            if (e == cudaSuccess)
+                e = launch_gather_pops_sparse_aa<T>(d_cur, qstride, d_label, d_index, d_sid, box, own_z0, own_z1, fluid_label,
+                                                    compact_first, (long long)n, (int)(steps & 1), tmp, st);
+            launches++;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(f, tmp, n * Q * sizeof(T), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(tmp);
+            CK(e);
+            return 0;
+        }
         if (sparse) {  // d_scr itself, q-major
             for (int q = 0; q < Q; q++)
                 CK(cudaMemcpyAsync((T *)f + (size_t)q * n, d_cur + (size_t)q * qstride + n_lo_stored, n * sizeof(T),
@@ -1571,7 +1652,44 @@ struct Solver final : SolverBase {
     int sync() override {
         CK(cudaSetDevice(d.device));
         CK(cudaStreamSynchronize(st));
+        return check_sync_error();
+    }
+    // ---- self-checking build (tools/selfcheck.py)
+    unsigned long long *d_chk_shadow[2] = {nullptr, nullptr}, *d_chk_count = nullptr;
+    size_t chk_elems = 0;
+    unsigned int chk_launch_id = 0;
+    int chk_prepare() {
+        const size_t elems = sparse ? (size_t)qstride * Q + 64 : (size_t)qstride * Q + (size_t)box.plane + box.px + 64;
+        if (d_chk_count && elems == chk_elems) return 0;
+        for (auto &p : d_chk_shadow)
+            if (p) cudaFree(p), p = nullptr;
+        if (!d_chk_count) {
+            CK(cudaMalloc((void **)&d_chk_count, 2 * sizeof(unsigned long long)));
+            CK(cudaMemset(d_chk_count, 0, 2 * sizeof(unsigned long long)));
+        }
+        for (int b = 0; b < (d_fb == d_fa ? 1 : 2); b++) {
+            CK(cudaMalloc((void **)&d_chk_shadow[b], elems * sizeof(unsigned long long)));
+            CK(cudaMemset(d_chk_shadow[b], 0, elems * sizeof(unsigned long long)));
+        }
+        chk_elems = elems;
         return 0;
+    }
+    int selfcheck(uint64_t *out2) override {
+#ifdef LBM_SELFCHECK
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(st));
+        out2[0] = out2[1] = 0;
+        if (d_chk_count) {
+            unsigned long long v[2];
+            CK(cudaMemcpy(v, d_chk_count, sizeof v, cudaMemcpyDeviceToHost));
+            out2[0] = v[0], out2[1] = v[1];
+        }
+        out2[2] = chk_launch_id;
+        return 0;
+#else
+        (void)out2;
+        FAIL(LBM_ERR_STATE, "not a self-checking build (compile with -DLBM_SELFCHECK, tools/selfcheck.py)");
+#endif
     }
     void *stream_ptr() override { return (void *)st; }
 };
@@ -1803,6 +1921,7 @@ int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *b
     return h->s->sync_export(handle, ptr, byte_offset);
 }
 int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync) { H_OR_FAIL; return h->s->sync_attach(side, peer_sync); }
+int lbm_debug_selfcheck(lbm_handle h, uint64_t out[3]) { H_OR_FAIL; return out ? h->s->selfcheck(out) : LBM_ERR_ARG; }
 int lbm_write_bc_csv(lbm_handle h, const char *path) { H_OR_FAIL; return path ? h->s->write_bc_csv(path) : LBM_ERR_ARG; }
 
 // ============================================================================

@@ -358,20 +358,22 @@ __global__ void k_init(const __grid_constant__ InitParams<T> p) {
 }
 
 // ---------------------------------------------------------------- gathers
+// `sid` (optional): the moment arrays are not box-dense but numbered by sid[cell] (in-place sparse storage)
 template <typename T>
 __global__ void k_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
-                                const int32_t *index, Box b, long long c0, long long c1, int fluid_label, long long first,
-                                T *orho, T *oux, T *ouy, T *ouz) {
+                                const int32_t *index, const int32_t *sid, Box b, long long c0, long long c1, int fluid_label,
+                                long long first, T *orho, T *oux, T *ouy, T *ouz) {
     long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
     int i = index[c];
     if (i < 0) return;
     long long o = (long long)i - first;
     bool fl = label[c] == fluid_label;
-    orho[o] = fl ? rho[c] : T(0);
-    oux[o] = fl ? ux[c] : T(0);
-    ouy[o] = fl ? uy[c] : T(0);
-    ouz[o] = fl ? uz[c] : T(0);
+    const long long e = (fl && sid) ? (long long)sid[c] : c;
+    orho[o] = fl ? rho[e] : T(0);
+    oux[o] = fl ? ux[e] : T(0);
+    ouy[o] = fl ? uy[e] : T(0);
+    ouz[o] = fl ? uz[e] : T(0);
 }
 template <typename T>
 __global__ void k_gather_pops(const T *f, long long qstride, const int32_t *index, Box b, long long c0, long long c1,
@@ -472,13 +474,42 @@ __global__ void k_halo_unpack(T *f, long long qstride, const int8_t *label8, int
 //           base + l; [0] is the chunk's first id), [19] first lane | length << 8 (0 = no
 //           piece), [20],[21] Cartesian cell id of lane 0 (lo, hi), [22] 1 if any node of
 //           the piece has a boundary link, [23] unused.
+// row_src(r): source offset of the 8 neighbouring rows, as the direction with c_x = 0 in that row
+__device__ __forceinline__ int row_src_dir(int r) {
+    const int a[8] = {3, 4, 5, 6, 15, 16, 17, 18};
+    return a[r];
+}
+constexpr int ROW_INVALID = INT32_MIN;
+// id of the node at THIS lane's x in neighbouring row r, derived from any fluid source the lane has there
+// (x, x-1, x+1 for the rows that hold three directions); ROW_INVALID when the lane has no fluid source in that row
+__device__ __forceinline__ int row_anchor(const int32_t *sid, const int32_t *label, const Box &b, int fluid_label,
+                                          long long cartc, int r) {
+    const int k = row_src_dir(r);
+    const long long c0 = cartc - ((long long)b.px * cyq(k) + b.plane * czq(k));
+    const int x = (int)(cartc % b.px);
+    const int ndx = r < 4 ? 3 : 1;
+    for (int t = 0; t < ndx; t++) {
+        const int dx = t == 0 ? 0 : (t == 1 ? -1 : 1);
+        if (x + dx < 0 || x + dx >= b.nx) continue;
+        if (label[c0 + dx] == fluid_label) return sid[c0 + dx] - dx;
+    }
+    return ROW_INVALID;
+}
 struct ChunkScan {
     bool fluid, start;
     long long cartc;
     int my_rec, my_slot, nrec;
 };
+// rows != nullptr (in-place storage, own numbering): a piece additionally ends where, in one of the 8
+// neighbouring rows, the fluid sources stop being one consecutive id range (anchors[r] receives this
+// lane's id of "the node at my x" in row r, or ROW_INVALID)
+struct RowInfo {
+    const int32_t *sid, *label;
+    int fluid_label;
+};
 __device__ __forceinline__ ChunkScan scan_chunk(const uint32_t *nodec, const long long *cart, Box b, long long i,
-                                                long long id0, long long id1) {
+                                                long long id0, long long id1, const RowInfo *rows = nullptr,
+                                                int *anchors = nullptr) {
     const int lane = threadIdx.x & 31;
     ChunkScan r;
     const bool valid = i >= id0 && i < id1;
@@ -488,6 +519,24 @@ __device__ __forceinline__ ChunkScan scan_chunk(const uint32_t *nodec, const lon
     const bool prev_f = __shfl_up_sync(0xffffffffu, r.fluid ? 1 : 0, 1) != 0;
     const bool joined = lane > 0 && prev_f && prev_c == r.cartc - 1 && (r.cartc % b.px) != 0;
     r.start = r.fluid && !joined;
+    if (rows) {
+        const unsigned starts = __ballot_sync(0xffffffffu, r.start);
+        const unsigned le = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u), lt = (1u << lane) - 1u;
+        const unsigned mine = starts & le;
+        const int rs = mine ? 31 - __clz(mine) : 0;  // first lane of my run
+        bool brk = false;
+        for (int rr = 0; rr < 8; rr++) {
+            const int v = r.fluid ? row_anchor(rows->sid, rows->label, b, rows->fluid_label, r.cartc, rr) : ROW_INVALID;
+            const int val = v == ROW_INVALID ? ROW_INVALID : v - lane;  // constant along a consecutive id range
+            anchors[rr] = val;
+            const unsigned V = __ballot_sync(0xffffffffu, val != ROW_INVALID);
+            const unsigned prev = V & lt & ~((1u << rs) - 1u);
+            const int lp = prev ? 31 - __clz(prev) : 0;
+            const int other = __shfl_sync(0xffffffffu, val, lp);
+            if (r.fluid && val != ROW_INVALID && prev && other != val) brk = true;
+        }
+        r.start = r.start || brk;
+    }
     const long long plane = r.fluid ? r.cartc / b.plane : -1;
     unsigned remaining = __ballot_sync(0xffffffffu, r.start);
     r.my_rec = 0, r.my_slot = 0, r.nrec = 0;
@@ -546,6 +595,53 @@ __global__ void k_seg_fill(const uint32_t *nodec, const long long *cart, const i
     o[23] = 0;
     if (r.my_slot == 0) atomicMin(plane_seg + (r.cartc / b.plane - own_zl0), seg);
 }
+// Records of the in-place storage: same layout as k_seg_fill, but per piece only the EIGHT row ids are
+// filled in (slot of the c_x = 0 direction of each row: base + lane = id of the node at the lane's x in
+// that row), taken from the first lane of the piece that has a fluid source in the row.
+__global__ void k_seg_count_rows(const uint32_t *nodec, const long long *cart, RowInfo rows, Box b, long long base_id,
+                                 long long id0, long long id1, int32_t *counts) {
+    const long long i = base_id + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int anchors[8];
+    const ChunkScan r = scan_chunk(nodec, cart, b, i, id0, id1, &rows, anchors);
+    if ((threadIdx.x & 31) == 0 && i < id1) counts[(i - base_id) >> 5] = r.nrec;
+}
+__global__ void k_seg_fill_rows(const uint32_t *nodec, const long long *cart, RowInfo rows, Box b, int own_zl0,
+                                long long base_id, long long id0, long long id1, const long long *chunk_offset,
+                                int32_t *rec, long long *plane_seg) {
+    const long long i = base_id + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int anchors[8];
+    const ChunkScan r = scan_chunk(nodec, cart, b, i, id0, id1, &rows, anchors);
+    const unsigned cont = __ballot_sync(0xffffffffu, r.fluid && !r.start);
+    const bool has_link = r.fluid ? (nodec[i] & NODE_LINKS) != 0 : false;
+    const unsigned links = __ballot_sync(0xffffffffu, has_link);
+    int len = 1;
+    if (lane < 31) {
+        const unsigned after = (~cont) >> (lane + 1);  // first lane after me that does not continue my piece
+        len = 1 + (after ? __ffs(after) - 1 : 31 - lane);
+        if (len > 32 - lane) len = 32 - lane;
+    }
+    const unsigned piece = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << lane;
+    int base[8];
+    for (int rr = 0; rr < 8; rr++) {  // every lane takes part in the shuffles; only piece starts use the result
+        const unsigned V = __ballot_sync(0xffffffffu, anchors[rr] != ROW_INVALID) & piece;
+        const int lp = V ? __ffs(V) - 1 : lane;
+        const int v = __shfl_sync(0xffffffffu, anchors[rr], lp);
+        base[rr] = (V && r.start) ? v : 0;
+    }
+    if (!r.start) return;  // one thread per piece: its first lane
+    const long long seg = chunk_offset[(i - base_id) >> 5] + r.my_rec;
+    int32_t *o = rec + seg * SEG_REC + r.my_slot * SEG_HALF;
+    for (int q = 0; q < SEG_HALF; q++) o[q] = 0;
+    o[0] = (int32_t)(i - lane);
+    for (int rr = 0; rr < 8; rr++) o[row_src_dir(rr)] = base[rr];
+    o[19] = lane | (len << 8);
+    const long long c_lane0 = r.cartc - lane;
+    o[20] = (int32_t)(c_lane0 & 0xffffffffLL);
+    o[21] = (int32_t)(c_lane0 >> 32);
+    o[22] = (links & piece) ? 1 : 0;
+    if (r.my_slot == 0) atomicMin(plane_seg + (r.cartc / b.plane - own_zl0), seg);
+}
 // exclusive scan of int32 counts into int64 offsets (single block, carry across chunks)
 __global__ void k_scan_i32(const int32_t *counts, long long *offsets, long long n, long long *total_out) {
     __shared__ long long carry;
@@ -585,20 +681,86 @@ __global__ void k_init_sparse(const __grid_constant__ InitParams<T> p, const lon
     const long long c = cart[i];
     Coord co = coord_of(b, c);
     T ux, uy, uz, feq[Q];
-    init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, p.label[c], co.x, co.y, co.z, ux, uy, uz);
-    if (p.case_rule == LBM_CASE_LDC) {
-        feq_all_ldc_init<T>(T(1.0), ux, uy, uz, feq);
-    } else {
-        const T r3 = T(1.0) / T(3.0), r18 = T(1.0) / T(18.0), r36 = T(1.0) / T(36.0);
+    if (p.aa && p.label[c] == p.fluid_label) {
+        // in-place storage: slot (q, x) of a fluid node holds what its first (even) step reads, the
+        // PRE-STREAMED population feq_q of the source x - c_q (every source of a fluid node is stored)
 #pragma unroll
-        for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+        for (int q = 0; q < Q; q++) {
+            const int x = co.x - cxq(q), y = co.y - cyq(q), z = co.z - czq(q);
+            const bool in = x >= 0 && x < b.nx && y >= 0 && y < b.ny && z >= b.z0 && z < b.z1;
+            const int g = in ? p.label[cell_of(b, x, y, z)] : 0;
+            init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, g, in ? x : -1, y, z, ux, uy, uz);
+            feq[q] = init_feq_q<T>(p.case_rule, q, T(1.0), ux, uy, uz);
+        }
+    } else {
+        init_velocity<T>(p.case_rule, p.u_max, p.bc, p.plane_in, p.plane_out, b, p.label[c], co.x, co.y, co.z, ux, uy, uz);
+        if (p.case_rule == LBM_CASE_LDC) {
+            feq_all_ldc_init<T>(T(1.0), ux, uy, uz, feq);
+        } else {
+            const T r3 = T(1.0) / T(3.0), r18 = T(1.0) / T(18.0), r36 = T(1.0) / T(36.0);
+#pragma unroll
+            for (int q = 0; q < Q; q++) feq[q] = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; q++) {
         p.fa[(long long)q * p.qstride + i] = feq[q];
-        p.fb[(long long)q * p.qstride + i] = feq[q];
+        if (p.fb != p.fa) p.fb[(long long)q * p.qstride + i] = feq[q];
     }
     p.rho[i] = T(0), p.ux[i] = T(0), p.uy[i] = T(0), p.uz[i] = T(0);
+}
+// in-place sparse storage seen as the reference's d_scr: entry (q, s) = what the fluid node x = s + c_q pulls next.
+// Before an even step that is a[q][x]; before an odd step a[opp q][s] when s is fluid, else the link's own slot a[q][x].
+// One thread per cell of the owned planes; `sid` is the storage's own numbering, `index` the reference's.
+template <typename T>
+__global__ void k_gather_pops_sparse_aa(const T *a, long long qstride, const int32_t *label, const int32_t *index,
+                                        const int32_t *sid, Box b, int fluid_label, long long first, long long c0,
+                                        long long c1, long long n, int odd, T *out) {
+    const long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const int ci = index[c];
+    if (ci < 0) return;
+    const long long t = (long long)ci - first;
+    const Coord co = coord_of(b, c);
+    const bool s_fluid = label[c] == fluid_label;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int x = co.x + cxq(q), y = co.y + cyq(q), z = co.z + czq(q);
+        T v = T(0);
+        if (x >= 0 && x < b.nx && y >= 0 && y < b.ny && z >= b.z0 && z < b.z1) {
+            const long long cx = cell_of(b, x, y, z);
+            if (label[cx] == fluid_label) {
+                const long long xi = sid[cx];
+                v = !odd ? a[(long long)q * qstride + xi] : (s_fluid ? a[(long long)oppq(q) * qstride + sid[c]] : a[(long long)q * qstride + xi]);
+            }
+        }
+        out[(long long)q * n + t] = v;
+    }
+}
+// ---- the in-place sparse storage's own numbering -----------------------------------------------------------
+// Only fluid nodes carry state there (boundary links live in the fluid node's own slot), so only they get
+// an id -- plus the single solid cells that sit between two fluid cells of a row ("F S F"): with those
+// filled in, the ids of the up-to-three sources a node has in a neighbouring row (x-1, x, x+1) are
+// always consecutive, i.e. ONE id per neighbouring row describes them.  Ids run over z, y, x like the
+// reference's index_transform, so a z-plane is one contiguous id range.
+__global__ void k_span_flags(const int32_t *label, Box b, int fluid_label, int32_t *keep) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.cells()) return;
+    const int x = (int)(c % b.px);
+    int k = 0;
+    if (x < b.nx) {
+        if (label[c] == fluid_label) k = 1;
+        else if (x > 0 && x < b.nx - 1 && label[c - 1] == fluid_label && label[c + 1] == fluid_label) k = 1;
+    }
+    keep[c] = k;
+}
+// per aligned chunk of 32 ids: which lanes are fluid, and whether any of them has a link that is not a wall
+__global__ void k_chunk_meta(const uint32_t *nodec, long long ns, uint2 *meta) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t node = i < ns ? nodec[i] : NODE_SKIP;
+    const unsigned fl = __ballot_sync(0xffffffffu, !(node & NODE_SKIP));
+    const unsigned sp = __ballot_sync(0xffffffffu, !(node & NODE_SKIP) && (node & NODE_LINKS) && !(node & NODE_WALLS_ONLY));
+    if ((threadIdx.x & 31) == 0 && i < ns) meta[i >> 5] = make_uint2(fl, sp ? 1u : 0u);
 }
 // reductions over compact arrays (see k_reduce_fields)
 template <typename T>
@@ -725,11 +887,11 @@ cudaError_t launch_init(const InitParams<T> &p, cudaStream_t s) {
 }
 template <typename T>
 cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
-                                 const int32_t *index, Box box, int own_z0, int own_z1, int fluid_label, long long first,
-                                 T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s) {
+                                 const int32_t *index, const int32_t *sid, Box box, int own_z0, int own_z1, int fluid_label,
+                                 long long first, T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s) {
     long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
     if (c1 <= c0) return cudaSuccess;
-    k_gather_fields<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(rho, ux, uy, uz, label, index, box, c0, c1, fluid_label,
+    k_gather_fields<T><<<nblocks(c1 - c0, 256), 256, 0, s>>>(rho, ux, uy, uz, label, index, sid, box, c0, c1, fluid_label,
                                                             first, orho, oux, ouy, ouz);
     return cudaGetLastError();
 }
@@ -832,6 +994,33 @@ cudaError_t launch_build_segments(const uint32_t *nodec, const long long *cart, 
     }
     return cudaGetLastError();
 }
+// in-place storage: the same two passes with the row-break rule and row ids (k_seg_*_rows)
+cudaError_t launch_build_segments_rows(const uint32_t *nodec, const long long *cart, const int32_t *sid, const int32_t *label,
+                                       int fluid_label, Box box, int own_zl0, long long id0, long long id1, int32_t *counts,
+                                       long long *offsets, long long *nseg_dev, int32_t *rec, long long *plane_seg,
+                                       cudaStream_t s) {
+    const long long base_id = id0 & ~31LL;
+    const long long nchunks = (id1 - base_id + 31) >> 5;
+    if (nchunks <= 0) return cudaSuccess;
+    RowInfo rows{sid, label, fluid_label};
+    if (!rec) {
+        k_seg_count_rows<<<nblocks(nchunks * 32, 256), 256, 0, s>>>(nodec, cart, rows, box, base_id, id0, id1, counts);
+        k_scan_i32<<<1, SCAN_BLOCK, 0, s>>>(counts, offsets, nchunks, nseg_dev);
+    } else {
+        k_seg_fill_rows<<<nblocks(nchunks * 32, 256), 256, 0, s>>>(nodec, cart, rows, box, own_zl0, base_id, id0, id1, offsets,
+                                                                   rec, plane_seg);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_span_flags(const int32_t *label, Box box, int fluid_label, int32_t *keep, cudaStream_t s) {
+    k_span_flags<<<nblocks(box.cells(), 256), 256, 0, s>>>(label, box, fluid_label, keep);
+    return cudaGetLastError();
+}
+cudaError_t launch_chunk_meta(const uint32_t *nodec, long long ns, uint2 *meta, cudaStream_t s) {
+    if (ns <= 0) return cudaSuccess;
+    k_chunk_meta<<<nblocks(((ns + 31) / 32) * 32, 256), 256, 0, s>>>(nodec, ns, meta);
+    return cudaGetLastError();
+}
 cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, const uint32_t *wall, const int32_t *label,
                                 long long cells, long long id_first, long long *cart, uint32_t *nodec, uint32_t *wallc,
                                 int8_t *labelc, cudaStream_t s) {
@@ -842,6 +1031,16 @@ template <typename T>
 cudaError_t launch_init_sparse(const InitParams<T> &p, const long long *cart, long long nstored, cudaStream_t s) {
     if (nstored <= 0) return cudaSuccess;
     k_init_sparse<T><<<nblocks(nstored, 128), 128, 0, s>>>(p, cart, nstored);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_gather_pops_sparse_aa(const T *a, long long qstride, const int32_t *label, const int32_t *index,
+                                         const int32_t *sid, Box box, int own_z0, int own_z1, int fluid_label, long long first,
+                                         long long n, int odd, T *out, cudaStream_t s) {
+    const long long c0 = (long long)(own_z0 - box.z0) * box.plane, c1 = (long long)(own_z1 - box.z0) * box.plane;
+    if (n <= 0 || c1 <= c0) return cudaSuccess;
+    k_gather_pops_sparse_aa<T><<<nblocks(c1 - c0, 128), 128, 0, s>>>(a, qstride, label, index, sid, box, fluid_label, first, c0,
+                                                                     c1, n, odd, out);
     return cudaGetLastError();
 }
 template <typename T>
@@ -872,14 +1071,17 @@ cudaError_t launch_halo_unpack_sparse(T *f, long long qstride, const int8_t *lab
 #define LBM_INST(T)                                                                                                     \
     template cudaError_t launch_init<T>(const InitParams<T> &, cudaStream_t);                                           \
     template cudaError_t launch_gather_fields<T>(const T *, const T *, const T *, const T *, const int32_t *,           \
-                                                 const int32_t *, Box, int, int, int, long long, T *, T *, T *, T *,    \
-                                                 cudaStream_t);                                                         \
+                                                 const int32_t *, const int32_t *, Box, int, int, int, long long, T *,  \
+                                                 T *, T *, T *, cudaStream_t);                                          \
     template cudaError_t launch_gather_pops<T>(const T *, long long, const int32_t *, Box, int, int, long long,         \
                                                long long, int, T *, cudaStream_t);                                           \
     template cudaError_t launch_reduce_fields<T>(const T *, const T *, const T *, const int32_t *, Box, int, int, int,  \
                                                  int, int, double *, cudaStream_t);                                     \
     template cudaError_t launch_halo_pack<T>(const T *, long long, Box, int, int, T *, cudaStream_t);                   \
     template cudaError_t launch_init_sparse<T>(const InitParams<T> &, const long long *, long long, cudaStream_t);      \
+    template cudaError_t launch_gather_pops_sparse_aa<T>(const T *, long long, const int32_t *, const int32_t *,        \
+                                                         const int32_t *, Box, int, int, int, long long, long long,     \
+                                                         int, T *, cudaStream_t);                                       \
     template cudaError_t launch_reduce_fields_sparse<T>(const T *, const T *, const T *, const int8_t *,                \
                                                         const long long *, Box, long long, long long, int, int, int,   \
                                                         double *, cudaStream_t);                                        \

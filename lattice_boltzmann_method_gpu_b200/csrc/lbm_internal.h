@@ -83,8 +83,15 @@ struct StepParams {
     const T *pull_base[Q];
     T *store_base[Q];
     T *slot_base[Q];                // slot_base[q][c]: where cell c leaves the boundary value of its link q
-    int case_rule;                  // lbm_case_rule (initial-state rule, for static links in the AA odd step)
+    int case_rule;                  // lbm_case_rule
     T u_init;                       // lbm_case_desc.u_max
+    // self-checking build (-DLBM_SELFCHECK, tools/selfcheck.py; compute-sanitizer is not available on the GPU
+    // pool): every population access of the step kernels is checked against the handle's buffers, and a
+    // shadow word per element records which thread touched it in this launch
+    const T *chk_lo[2], *chk_hi[2];     // the population buffers [lo, hi)
+    unsigned long long *chk_shadow[2];  // (launch id << 32) | (thread + 1) per buffer element
+    unsigned long long *chk_count;      // [0] accesses outside the buffers, [1] elements touched by two threads in one launch
+    unsigned int chk_launch;
 };
 
 template <typename T>
@@ -99,6 +106,7 @@ struct InitParams {
     T u_max;
     BcEntry bc[LBM_MAX_BC];
     const T *plane_in, *plane_out;
+    int fluid_label;
 };
 
 // ---- launchers implemented in the .cu files ----
@@ -123,8 +131,8 @@ template <typename T>
 cudaError_t launch_init(const InitParams<T> &p, cudaStream_t s);
 template <typename T>
 cudaError_t launch_gather_fields(const T *rho, const T *ux, const T *uy, const T *uz, const int32_t *label,
-                                 const int32_t *index, Box box, int own_z0, int own_z1, int fluid_label, long long first,
-                                 T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s);
+                                 const int32_t *index, const int32_t *sid, Box box, int own_z0, int own_z1, int fluid_label,
+                                 long long first, T *orho, T *oux, T *ouy, T *ouz, cudaStream_t s);
 // layout: 0 two-buffer (slot q of cell y), 1 AA before an even step (a[q][y+c_q]), 2 AA before an odd step (a[opp q][y])
 template <typename T>
 cudaError_t launch_gather_pops(const T *f, long long qstride, const int32_t *index, Box box, int own_z0, int own_z1,
@@ -159,6 +167,19 @@ cudaError_t launch_compact_maps(const int32_t *index, const uint32_t *node, cons
                                 int8_t *labelc, cudaStream_t s);
 template <typename T>
 cudaError_t launch_init_sparse(const InitParams<T> &p, const long long *cart, long long nstored, cudaStream_t s);
+// debug view of the in-place sparse storage as the reference's d_scr: out[q][s] = the population the fluid
+// node s + c_q pulls next (0 when that node is not fluid)
+template <typename T>
+cudaError_t launch_gather_pops_sparse_aa(const T *a, long long qstride, const int32_t *label, const int32_t *index,
+                                         const int32_t *sid, Box box, int own_z0, int own_z1, int fluid_label, long long first,
+                                         long long n, int odd, T *out, cudaStream_t s);
+// the in-place sparse storage's own numbering (fluid nodes + single-cell x gaps), its records and chunk masks
+cudaError_t launch_span_flags(const int32_t *label, Box box, int fluid_label, int32_t *keep, cudaStream_t s);
+cudaError_t launch_chunk_meta(const uint32_t *nodec, long long ns, uint2 *meta, cudaStream_t s);
+cudaError_t launch_build_segments_rows(const uint32_t *nodec, const long long *cart, const int32_t *sid, const int32_t *label,
+                                       int fluid_label, Box box, int own_zl0, long long id0, long long id1, int32_t *counts,
+                                       long long *offsets, long long *nseg_dev, int32_t *rec, long long *plane_seg,
+                                       cudaStream_t s);
 template <typename T>
 cudaError_t launch_reduce_fields_sparse(const T *ux, const T *uy, const T *uz, const int8_t *labelc, const long long *cart,
                                         Box box, long long i0, long long i1, int kind, int fluid_label, int case_rule,
@@ -179,6 +200,12 @@ struct SparseParams {
     const uint32_t *wallc;   // wall masks by compact id
     long long seg_begin, seg_end;
     int spw;                 // consecutive records per warp
+    // in-place sparse storage (step_sparse_aa.cuh)
+    const long long *cartc;  // Cartesian cell of a compact id (boundary slow path)
+    const uint2 *cmeta;      // per aligned chunk of 32 ids: fluid-lane mask, "some lane has a non-wall link"
+    long long id_begin, id_end;  // compact ids of the even (local) step's launch
+    int halo_lo_n, halo_hi0;     // local ids < halo_lo_n lie in the low halo plane, ids >= halo_hi0 in the high one
+    int dk[Q];                   // (k - opp k) * qstride: from the array of opp(k) to the same node's slot in the array of k
 };
 
 // fused step (lbm_step_fast.cu / lbm_step_strict.cu)
@@ -186,6 +213,10 @@ template <typename T>
 cudaError_t launch_step_sparse_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_sparse_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
+template <typename T>
+cudaError_t launch_step_sparse_aa_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
+template <typename T>
+cudaError_t launch_step_sparse_aa_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s);
 template <typename T>

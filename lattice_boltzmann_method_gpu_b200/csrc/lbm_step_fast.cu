@@ -20,3 +20,13 @@ cudaError_t launch_step_sparse_fast(const SparseParams<T> &p, bool moments, bool
 template cudaError_t launch_step_sparse_fast<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
 template cudaError_t launch_step_sparse_fast<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
 }  // namespace lbm
+
+#include "step_sparse_aa.cuh"
+namespace lbm {
+template <typename T>
+cudaError_t launch_step_sparse_aa_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
+    return launch_step_sparse_aa_impl<T, false>(p, moments, resid, s);
+}
+template cudaError_t launch_step_sparse_aa_fast<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
+template cudaError_t launch_step_sparse_aa_fast<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+}  // namespace lbm

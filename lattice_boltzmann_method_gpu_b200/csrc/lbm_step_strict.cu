@@ -24,3 +24,13 @@ cudaError_t launch_step_sparse_strict(const SparseParams<T> &p, bool moments, bo
 template cudaError_t launch_step_sparse_strict<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
 template cudaError_t launch_step_sparse_strict<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
 }  // namespace lbm
+
+#include "step_sparse_aa.cuh"
+namespace lbm {
+template <typename T>
+cudaError_t launch_step_sparse_aa_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s) {
+    return launch_step_sparse_aa_impl<T, true>(p, moments, resid, s);
+}
+template cudaError_t launch_step_sparse_aa_strict<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
+template cudaError_t launch_step_sparse_aa_strict<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+}  // namespace lbm

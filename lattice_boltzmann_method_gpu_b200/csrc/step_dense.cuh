@@ -40,6 +40,33 @@ __device__ __forceinline__ T ld_stream(const T *p) {
     return __ldg(p);
 }
 
+// Self-checking build: LBM_CHK(p, address) in front of every population access of the step kernels.
+//  - the address must lie inside one of the handle's population buffers (guards included);
+//  - within one launch an element may be touched by ONE thread only -- the property that makes the
+//    in-place (AA) step race-free and lets the two-buffer step write boundary slots without atomics.
+// A normal build compiles the macro away.
+#ifdef LBM_SELFCHECK
+template <typename T>
+__device__ __noinline__ void chk_touch(const StepParams<T> &p, const T *a, bool track = true) {
+    if (!p.chk_count) return;
+    for (int b = 0; b < 2; b++)
+        if (a >= p.chk_lo[b] && a < p.chk_hi[b]) {
+            if (!track) return;  // a speculative read whose value is dropped: only its address matters
+            const unsigned long long tag = ((unsigned long long)p.chk_launch << 32) |
+                                           (unsigned long long)((unsigned)blockIdx.x * blockDim.x + threadIdx.x + 1u);
+            const unsigned long long old = atomicExch(p.chk_shadow[b] + (a - p.chk_lo[b]), tag);
+            if ((old >> 32) == p.chk_launch && old != tag) atomicAdd(p.chk_count + 1, 1ull);
+            return;
+        }
+    atomicAdd(p.chk_count, 1ull);
+}
+#define LBM_CHK(p_, a_) chk_touch(p_, a_)
+#define LBM_CHK_BOUNDS(p_, a_) chk_touch(p_, a_, false)
+#else
+#define LBM_CHK(p_, a_) ((void)0)
+#define LBM_CHK_BOUNDS(p_, a_) ((void)0)
+#endif
+
 // prescribed boundary speed of BC entry `e` at boundary node (gx, gy, gz) (global coords)
 template <typename T>
 __device__ __forceinline__ T bc_speed(const StepParams<T> &p, const BcEntry &e, int gx, int gz) {
@@ -273,7 +300,10 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
         if (rest && !(node & NODE_HAS_BC)) {
 #pragma unroll
             for (int q = 1; q < Q; q++)
-                if (rest & (1u << q)) p.slot_base[q][c] = f[q];
+                if (rest & (1u << q)) {
+                    LBM_CHK(p, p.slot_base[q] + c);
+                    p.slot_base[q][c] = f[q];
+                }
         } else if (rest) {
             keep_pre = true;
 #pragma unroll
@@ -287,8 +317,12 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
             // push only into fluid targets: x + c_q is the source of link opp(q); a target beyond a
             // slab face lives in the neighbour's memory (push_to_peers)
             const bool remote = (czq(q) > 0 && p.peer_up) || (czq(q) < 0 && p.peer_dn);
-            if (q == 0 || (!(node & (1u << oppq(q))) && !remote)) p.store_base[q][c] = f[q];
+            if (q == 0 || (!(node & (1u << oppq(q))) && !remote)) {
+                LBM_CHK(p, p.store_base[q] + c);
+                p.store_base[q][c] = f[q];
+            }
         } else {
+            LBM_CHK(p, p.store_base[q] + c);
             p.store_base[q][c] = f[q];
         }
     }
@@ -303,7 +337,10 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
                                                      : ((WALL_READY || MODE != MODE_AB) ? (wallw & node & NODE_LINKS) : p.wall[c]);
 #pragma unroll
         for (int q = 1; q < Q; q++) {
-            if (wl & (1u << q)) p.slot_base[q][c] = f[oppq(q)];
+            if (wl & (1u << q)) {
+                LBM_CHK(p, p.slot_base[q] + c);
+                p.slot_base[q][c] = f[oppq(q)];
+            }
         }
         // what is left is an inlet/outlet/lid link (slow path) or a static link (handled above)
         const uint32_t rest = node & NODE_LINKS & ~wl;
@@ -318,7 +355,10 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
             const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, fpre, hv);
 #pragma unroll
             for (int q = 1; q < Q; q++) {
-                if (wm & (1u << q)) p.slot_base[q][c] = hv[q];
+                if (wm & (1u << q)) {
+                    LBM_CHK(p, p.slot_base[q] + c);
+                    p.slot_base[q][c] = hv[q];
+                }
             }
         }
     }
@@ -339,7 +379,12 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
         // every thread pulls; the buffers carry guards so all addresses are mapped
         node = p.node[c];
 #pragma unroll
-        for (int q = 0; q < Q; q++) f[q] = MODE == MODE_AB ? ld_spec(p.pull_base[q] + c) : ld_spec_rw(p.pull_base[q] + c);
+        for (int q = 0; q < Q; q++) {
+            // every thread pulls, a non-fluid one drops what it read: bounds always, ownership only when used
+            if (node & NODE_SKIP) LBM_CHK_BOUNDS(p, p.pull_base[q] + c);
+            else LBM_CHK(p, p.pull_base[q] + c);
+            f[q] = MODE == MODE_AB ? ld_spec(p.pull_base[q] + c) : ld_spec_rw(p.pull_base[q] + c);
+        }
         if (kind == SEG_EMPTY) return;
     } else {
         if (kind == SEG_EMPTY) return;
@@ -350,7 +395,10 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
     if (!(node & NODE_SKIP)) {
         if (!SPEC) {
 #pragma unroll
-            for (int q = 0; q < Q; q++) f[q] = MODE == MODE_AB ? ld_stream(p.pull_base[q] + c) : p.pull_base[q][c];
+            for (int q = 0; q < Q; q++) {
+                LBM_CHK(p, p.pull_base[q] + c);
+                f[q] = MODE == MODE_AB ? ld_stream(p.pull_base[q] + c) : p.pull_base[q][c];
+            }
         }
         finish_cell<T, STRICT, MOMENTS, RESID, MODE, !SPEC>(p, c, node, wallw, f, velsum);
     }

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
             for (int q = 0; q < Q; q++) {
                 const int bq = __shfl_sync(0xffffffffu, r0, q);
                 // idle lanes read their own (stored, unused) slot: no branch between the shuffles
+                if (active) LBM_CHK(p, p.pull_base[q] + (bq + lane));  // the idle lanes' dummy reads are not the pull
                 f[q] = ld_stream(p.pull_base[q] + (active ? bq + lane : i));
             }
         } else {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
                 const int ba = __shfl_sync(0xffffffffu, r0, q);
                 const int bb = SEG_HALF + q < 32 ? __shfl_sync(0xffffffffu, r0, SEG_HALF + q)
                                                  : __shfl_sync(0xffffffffu, r1, SEG_HALF + q - 32);
+                if (active) LBM_CHK(p, p.pull_base[q] + ((inB ? bb : ba) + lane));
                 f[q] = ld_stream(p.pull_base[q] + (active ? (inB ? bb : ba) + lane : i));
             }
         }
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
         if (active) {
             collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
 #pragma unroll
-            for (int q = 0; q < Q; q++) p.store_base[q][i] = f[q];
+            for (int q = 0; q < Q; q++) {
+                LBM_CHK(p, p.store_base[q] + i);
+                p.store_base[q][i] = f[q];
+            }
             if (MOMENTS) {
                 p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
             }
@@ -98,7 +103,10 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
                 wl = (node & NODE_WALLS_ONLY) ? (node & NODE_LINKS) : (wl & node & NODE_LINKS);
 #pragma unroll
                 for (int q = 1; q < Q; q++)
-                    if (wl & (1u << q)) p.store_base[q][mine[q] + lane] = f[oppq(q)];
+                    if (wl & (1u << q)) {
+                        LBM_CHK(p, p.store_base[q] + (mine[q] + lane));
+                        p.store_base[q][mine[q] + lane] = f[oppq(q)];
+                    }
                 const uint32_t rest = (node & NODE_HAS_BC) ? (node & NODE_LINKS & ~wl) : 0u;  // inlet/outlet; static links keep their slot
                 if (rest) {
                     const long long c = (long long)(((unsigned long long)chi << 32) | clo) + lane;  // Cartesian cell
@@ -108,7 +116,10 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
                     const uint32_t wm = boundary_node<T>(p, c, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv);
 #pragma unroll
                     for (int q = 1; q < Q; q++)
-                        if (wm & (1u << q)) p.store_base[q][mine[q] + lane] = hv[q];
+                        if (wm & (1u << q)) {
+                            LBM_CHK(p, p.store_base[q] + (mine[q] + lane));
+                            p.store_base[q][mine[q] + lane] = hv[q];
+                        }
                 }
             }
         }

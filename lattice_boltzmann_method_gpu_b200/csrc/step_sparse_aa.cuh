@@ -1,0 +1,239 @@
+// Fused step on the SPARSE IN-PLACE storage (LBM_STORE_SPARSE_AA): ONE population buffer in the
+// reference's compact order (index_transform numbering, bifurcation.cu:241-252), AA-pattern streaming
+// (Bailey et al. 2009), and every boundary link kept in the FLUID node's own slot.
+//
+//   even step (purely local):  f_k(x) = a[k][x]                      g_opp(k)(x) -> a[k][x]
+//   odd step:                  f_k(x) = a[opp k][x - c_k]            g_opp(k)(x) -> a[opp k][x - c_k]
+// i.e. each step reads and writes the SAME 19 addresses.  For a link k whose source x - c_k is not a
+// fluid node the odd step uses the even step's address a[k][x] as well -- the node's own slot:
+//   wall        : g_opp(k)(x) written there IS the half-way bounce-back value f_k(x) of the next step
+//                 (bif:655-798), so a wall link costs one address select and no extra store;
+//   inlet/outlet: the non-equilibrium extrapolation value (bif:877-1021) goes there instead of g_opp(k);
+//   static      : the slot is simply never written -- it keeps the initial equilibrium of its source.
+// Solid nodes are never read or written by a step (they only keep their place in the numbering), the
+// scattered partial-sector stores into wall slots of the two-buffer sparse kernel are gone, and the even
+// step needs no neighbour information at all: it is a straight pass over the compact arrays.
+//
+// The odd step takes neighbour ids from the same run-segment records as step_sparse.cuh, but only
+// EIGHT of the 19 base ids: in the compact order the sources of the three directions that share a
+// neighbouring row (same c_y, c_z) are consecutive ids, so one id per row -- that of the c_x = 0
+// direction -- gives all three.
+//
+// Across z-slabs (fused peer stores): the even step copies the crossing populations of a face-plane node
+// into the neighbour's halo replica of that node (slot opp q, what the neighbour's odd step pulls); the
+// odd step stores g for a target in the halo plane straight into the neighbour's owned plane instead.
+#pragma once
+#include "step_sparse.cuh"
+
+namespace lbm {
+
+// resident CTAs per SM (128 threads each) of the local (even) and of the neighbour (odd) step; the odd one
+// keeps 18 element indices next to the populations.  Measured choices: profiles/r02_notes.md
+#ifndef LBM_SPAA64_MINB
+#define LBM_SPAA64_MINB 6
+#endif
+#ifndef LBM_SPAA32_MINB
+#define LBM_SPAA32_MINB 10
+#endif
+#ifndef LBM_SPAA64_ODD_MINB
+#define LBM_SPAA64_ODD_MINB 6
+#endif
+#ifndef LBM_SPAA32_ODD_MINB
+#define LBM_SPAA32_ODD_MINB 10
+#endif
+
+// neighbouring rows (c_y, c_z) != (0,0) of D3Q19 and the direction with c_x = 0 in each
+__host__ __device__ constexpr int row_rep(int r) {
+    constexpr int a[8] = {3, 4, 5, 6, 15, 16, 17, 18};
+    return a[r];
+}
+__host__ __device__ constexpr int row_of(int k) {
+    constexpr int a[Q] = {-1, -1, -1, 0, 1, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3, 4, 5, 6, 7};
+    return a[k];
+}
+
+// inlet / outlet links of a node, after its collision: the extrapolated value goes into the own slot
+template <typename T>
+__device__ __forceinline__ void own_slot_bc(const StepParams<T> &p, long long cart, long long i, uint32_t rest, T rho, T ux,
+                                            T uy, T uz, const T (&f)[Q]) {
+    T gl[Q], hv[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) gl[q] = f[q];
+    // static links report no value (mode MODE_AB): their slot is left alone
+    const uint32_t wm = boundary_node<T>(p, cart, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv);
+#pragma unroll
+    for (int q = 1; q < Q; q++)
+        if (wm & (1u << q)) {
+            LBM_CHK(p, p.store_base[q] + i);
+            p.store_base[q][i] = hv[q];
+        }
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB : LBM_SPAA32_MINB)
+    k_sparse_aa_even(const __grid_constant__ SparseParams<T> sp) {
+    const StepParams<T> &p = sp.base;
+    const long long i = sp.id_begin + (long long)blockIdx.x * SPARSE_BLOCK + threadIdx.x;
+    double velsum = 0.0;
+    // one word per 32 ids says which lanes are fluid and whether any of them needs its node word at all
+    // (walls need nothing in the local step): 0.25 B of metadata per node instead of 4
+    uint2 cm = make_uint2(0u, 0u);
+    if (i < sp.id_end) cm = sp.cmeta[i >> 5];
+    if ((cm.x >> (i & 31)) & 1u) {
+        T f[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            LBM_CHK(p, p.pull_base[q] + i);
+            f[q] = p.pull_base[q][i];
+        }
+        uint32_t node = 0u, rest = 0u;  // rest: links that are neither fluid-fed nor walls: inlet / outlet / static
+        if (cm.y) node = sp.nodec[i];
+        if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
+        T rho, ux, uy, uz;
+        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+        if (rest == 0u) {
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                LBM_CHK(p, p.store_base[q] + i);
+                p.store_base[q][i] = f[oppq(q)];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; q++)
+                if (!(rest & (1u << q))) {
+                    LBM_CHK(p, p.store_base[q] + i);
+                    p.store_base[q][i] = f[oppq(q)];
+                }
+            if (node & NODE_HAS_BC) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f);
+        }
+        if (MOMENTS) {
+            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+        }
+        if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+        if (PEERS) push_to_peers<T, MODE_AA_EVEN>(p, i - p.face_c0, node, f);
+    }
+    if (RESID) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
+        if ((threadIdx.x & 31) == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    }
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_MINB : LBM_SPAA32_ODD_MINB)
+    k_sparse_aa_odd(const __grid_constant__ SparseParams<T> sp) {
+    const StepParams<T> &p = sp.base;
+    const int lane = threadIdx.x & 31;
+    const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
+    if (seg >= sp.seg_end) return;  // warp-uniform
+    const int32_t r0 = sp.rec[seg * SEG_REC + lane];
+    const int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
+    const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
+    const bool two = (mB >> 8) != 0;  // warp-uniform
+    const bool inB = two && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
+    const bool active = inB || (lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8));
+    const int i = __shfl_sync(0xffffffffu, r0, 0) + lane;  // compact id: the chunk's first id + lane in both pieces
+    // compact id of the node at this lane's x in each of the 8 neighbouring rows
+    int j[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int b = __shfl_sync(0xffffffffu, r0, row_rep(r));
+        if (two) {
+            const int bb = SEG_HALF + row_rep(r) < 32 ? __shfl_sync(0xffffffffu, r0, SEG_HALF + row_rep(r))
+                                                      : __shfl_sync(0xffffffffu, r1, SEG_HALF + row_rep(r) - 32);
+            b = inB ? bb : b;
+        }
+        j[r] = b + lane;
+    }
+    int has_links = __shfl_sync(0xffffffffu, r0, 22);
+    if (two) {
+        const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
+        has_links = inB ? bl : has_links;
+    }
+    double velsum = 0.0;
+    if (active) {
+        const uint32_t node = has_links ? sp.nodec[i] : 0u;
+        // ONE element index per direction, used for the load and for the store: inside the array of opp(k),
+        // either the source's id or -- for a link -- this node's own slot in the array of k, which lies
+        // dk[k] = (k - opp k) * qstride elements away
+        int idx[Q];
+        T f[Q];
+        LBM_CHK(p, p.pull_base[0] + i);
+        f[0] = p.pull_base[0][i];
+#pragma unroll
+        for (int k = 1; k < Q; k++) {
+            const int n = (k < 3 ? i : j[row_of(k) < 0 ? 0 : row_of(k)]) - cxq(k);
+            idx[k] = (node & (1u << k)) ? i + sp.dk[k] : n;
+            LBM_CHK(p, p.pull_base[oppq(k)] + idx[k]);
+            f[k] = p.pull_base[oppq(k)][idx[k]];
+        }
+        uint32_t rest = 0u;
+        if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
+        T rho, ux, uy, uz;
+        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+        LBM_CHK(p, p.store_base[0] + i);
+        p.store_base[0][i] = f[0];
+#pragma unroll
+        for (int k = 1; k < Q; k++) {
+            if (rest & (1u << k)) continue;  // inlet / outlet (written below) or static (kept) link
+            if (PEERS && !(node & (1u << k))) {
+                if (czq(k) > 0 && p.peer_dn && idx[k] < sp.halo_lo_n) {
+                    // the target x - c_k lies in the low halo plane: it is a node the neighbour below owns
+                    p.peer_dn[(long long)oppq(k) * p.peer_dn_qs + p.peer_dn_own + idx[k]] = f[oppq(k)];
+                    continue;
+                }
+                if (czq(k) < 0 && p.peer_up && idx[k] >= sp.halo_hi0) {
+                    p.peer_up[(long long)oppq(k) * p.peer_up_qs + p.peer_up_own + (idx[k] - sp.halo_hi0)] = f[oppq(k)];
+                    continue;
+                }
+            }
+            LBM_CHK(p, p.store_base[oppq(k)] + idx[k]);
+            p.store_base[oppq(k)][idx[k]] = f[oppq(k)];
+        }
+        if (rest && (node & NODE_HAS_BC)) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f);
+        if (MOMENTS) {
+            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+        }
+        if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+    }
+    if (RESID) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
+        if (lane == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    }
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
+cudaError_t launch_sparse_aa_mode(const SparseParams<T> &p, cudaStream_t s) {
+    if (p.base.parity == 0) {
+        const long long n = p.id_end - p.id_begin;
+        if (n <= 0) return cudaSuccess;
+        k_sparse_aa_even<T, STRICT, MOMENTS, RESID, PEERS><<<(unsigned)((n + SPARSE_BLOCK - 1) / SPARSE_BLOCK), SPARSE_BLOCK, 0, s>>>(p);
+    } else {
+        const long long nrec = p.seg_end - p.seg_begin;
+        if (nrec <= 0) return cudaSuccess;
+        const int wpb = SPARSE_BLOCK / 32;
+        k_sparse_aa_odd<T, STRICT, MOMENTS, RESID, PEERS><<<(unsigned)((nrec + wpb - 1) / wpb), SPARSE_BLOCK, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T, bool STRICT>
+cudaError_t launch_step_sparse_aa_impl(const SparseParams<T> &p_in, bool moments, bool resid, cudaStream_t s) {
+    SparseParams<T> p = p_in;
+    for (int q = 0; q < Q; q++) {
+        p.base.pull_base[q] = p.base.src + (long long)q * p.base.qstride;
+        p.base.store_base[q] = p.base.dst + (long long)q * p.base.qstride;
+        p.dk[q] = (int)((long long)(q - oppq(q)) * p.base.qstride);  // |q - opp q| <= 3, qstride < 2^31 / 3 (checked by the host)
+    }
+    const bool peers = p.base.peer_up || p.base.peer_dn;
+#define LBM_SPAA(M, R)                                                                    \
+    (peers ? launch_sparse_aa_mode<T, STRICT, M, R, true>(p, s) : launch_sparse_aa_mode<T, STRICT, M, R, false>(p, s))
+    if (moments && resid) return LBM_SPAA(true, true);
+    if (moments) return LBM_SPAA(true, false);
+    if (resid) return LBM_SPAA(false, true);
+    return LBM_SPAA(false, false);
+#undef LBM_SPAA
+}
+
+}  // namespace lbm

@@ -96,7 +96,7 @@ def test_random_masks_strict_parity(seed):
     o.initialize()
     o.step(30)
     fl = geo.ravel()[geo.ravel() != 0] == 4
-    for storage in (L.STORE_DENSE_AB, L.STORE_SPARSE_AB, L.STORE_DENSE_AA):
+    for storage in (L.STORE_DENSE_AB, L.STORE_SPARSE_AB, L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
         d = L.case_defaults(L.CASE_GEO_Y_INOUT)
         d.nz, d.ny, d.nx = flag.shape
         d.z_begin, d.z_end = 0, nz

@@ -34,11 +34,12 @@ def _group(name, n, P, L, storage, math=None, prec=None, out_dir=None):
 
 
 @pytest.mark.parametrize("name,n,P", [("ldc", 24, 3), ("ldc", 21, 5), ("pos", 24, 2), ("bif", None, 4), ("cor", None, 3)])
-@pytest.mark.parametrize("storage_name", ["dense_ab", "dense_aa", "sparse_ab"])
+@pytest.mark.parametrize("storage_name", ["dense_ab", "dense_aa", "sparse_ab", "sparse_aa"])
 def test_group_equals_single_domain_bitwise(name, n, P, storage_name):
     import lattice_boltzmann_method_gpu_b200 as L
 
-    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB}[storage_name]
+    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB,
+               "sparse_aa": L.STORE_SPARSE_AA}[storage_name]
     one = H.gpu_case(name, n, L.F64, L.MATH_FAST, storage=storage)
     nlat = H.gpu_setup(one, name)
     g = _group(name, n, P, L, storage)

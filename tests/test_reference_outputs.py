@@ -8,13 +8,15 @@ iteration at which the convergence loop stops, same residual log, same fields --
 files with byte-identical headers.
 
 Tolerance: the reference prints 6 significant digits and its kernels are compiled with FMA
-contraction, so fields are compared at 2e-5 of max|v|.  ldc is compared at 2e-3: its `update`
+contraction, so fields are compared at 2e-5 of max|v|.  ldc is compared at 1e-3: its `update`
 kernel bounces the walls in place while fluid nodes of the same launch read them (ldc.cu:75-313),
 so a fluid node sees a mix of this step's and two-steps-old wall values.  The stopping rule ends
 the run (k = 5119) while the flow is still 6.4e-2 away from its steady state; at that iteration
-the reference's field and ours differ by 7.6e-4 -- the same in fp32 and fp64, i.e. not rounding
-but that race -- 85x less than either differs from the converged field
-(tools/ldc_steady_probe.py, profiles/r01_notes.md)."""
+the reference's field and the defined semantics ("walls first", what the library implements bit
+for bit) differ by 7.6e-4.  tests/test_ldc_order_cpu.py accounts for that number: replaying the order
+ldc.cu's launch executes in brings the oracle to 3.4e-5 / 4.7e-5 of the real binary, which lies inside
+the envelope of the two order models; tests/test_reference_variants.py compares the library with the
+real binary at a true steady state, where the order no longer matters (5e-5, fp32 rounding)."""
 from pathlib import Path
 
 import numpy as np
@@ -93,7 +95,7 @@ def test_gpu_reproduces_reference_bifurcation_run(math_name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,rule,tol", [("ldc", 0, 2e-3), ("pos", 1, 2e-5)])
+@pytest.mark.parametrize("name,rule,tol", [("ldc", 0, 1e-3), ("pos", 1, 2e-5)])
 def test_gpu_reproduces_reference_convergence_runs(name, rule, tol, tmp_path):
     """ldc.cu:653-685 / Poiseulle.cu:986-1019: residual every step, stop after 51 hits of 1e-6"""
     import lattice_boltzmann_method_gpu_b200 as L

@@ -48,22 +48,23 @@ def _run(c, flag, steps):
         assert np.array_equal(r, g)
 
 
-@pytest.mark.parametrize("storage_name", ["sparse_ab", "dense_ab", "dense_aa"])
+@pytest.mark.parametrize("storage_name", ["sparse_ab", "sparse_aa", "dense_ab", "dense_aa"])
 def test_reinitialise_with_a_larger_mask(storage_name, tmp_path):
     """sparse buffers were sized for the first geometry only"""
     import lattice_boltzmann_method_gpu_b200 as L
 
-    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB}[storage_name]
+    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB,
+               "sparse_aa": L.STORE_SPARSE_AA}[storage_name]
     small, big = _tube_flag(40, 30, 40, 6.2), _tube_flag(40, 30, 40, 17.3)
     c = _bif_like(storage, small, L)
     c.desc.out_dir = str(tmp_path).encode()
     _run(c, small, 12)
     b0 = c.device_bytes
     _run(c, big, 12)   # about 8x the stored nodes
-    if storage_name == "sparse_ab":
+    if storage_name.startswith("sparse"):
         assert c.device_bytes > 2 * b0
     _run(c, small, 9)  # and back: fewer nodes than the host mirrors / records of the previous round
-    if storage_name == "sparse_ab":
+    if storage_name.startswith("sparse"):
         assert c.device_bytes <= b0 + 1024
 
 
@@ -89,14 +90,15 @@ def test_writer_follows_a_new_geometry(tmp_path):
     assert outs[0] == outs[1]
 
 
-@pytest.mark.parametrize("storage_name", ["dense_aa", "dense_ab", "sparse_ab"])
+@pytest.mark.parametrize("storage_name", ["dense_aa", "dense_ab", "sparse_ab", "sparse_aa"])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_static_link_from_a_moving_boundary_node(storage_name, prec):
     """a fluid node pulls a direction OUTSIDE the direction set of a label-5 node that was
     initialised with a nonzero velocity (cor.cu:302-306): that slot is a constant, feq_q(1, u0(s))"""
     import lattice_boltzmann_method_gpu_b200 as L
 
-    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB}[storage_name]
+    storage = {"dense_ab": L.STORE_DENSE_AB, "dense_aa": L.STORE_DENSE_AA, "sparse_ab": L.STORE_SPARSE_AB,
+               "sparse_aa": L.STORE_SPARSE_AA}[storage_name]
     dt = np.float32 if prec == "f32" else np.float64
     o, geo, idx, nlat = H.oracle_case("corstep", None, dt)
     for math in (L.MATH_STRICT, L.MATH_FAST):

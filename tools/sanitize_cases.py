@@ -1,8 +1,9 @@
-"""The step kernels under compute-sanitizer: every storage, both phases of the in-place
+"""The step kernels under a memory / race checker: every storage, both phases of the in-place
 storage, the speculative pull (which deliberately reads past rows into guard cells), boundary slow
 paths of all four case rules, and virtual z-slabs whose face launches store into another handle's
 buffers.  No torch, no oracle: only liblbm_b200.so through ctypes, so every kernel the tool sees is ours.
 
+  python tools/selfcheck.py          (the library's own self-checking build; what the GPU pool allows)
   compute-sanitizer --tool memcheck  --error-exitcode 7 python tools/sanitize_cases.py
   LBM_SPECULATIVE=1 compute-sanitizer --tool memcheck ... (forces the speculative pull, which small grids do not pick)
   compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_cases.py quick
@@ -19,6 +20,20 @@ import numpy as np  # noqa: E402
 
 import lattice_boltzmann_method_gpu_b200 as L  # noqa: E402
 from lattice_boltzmann_method_gpu_b200 import slab  # noqa: E402
+
+TOTAL = [0, 0, 0]  # out-of-range accesses, doubly touched elements, launches checked (self-checking build only)
+
+
+def tally(c, what):
+    try:
+        oob, races, launches = c.selfcheck()
+    except L.LbmError:
+        return
+    TOTAL[0] += oob
+    TOTAL[1] += races
+    TOTAL[2] += launches
+    print(f"   selfcheck {what}: out_of_range={oob} touched_by_two_threads={races} launches_checked={launches}", flush=True)
+
 
 
 def cases(quick):
@@ -44,6 +59,7 @@ def single(quick):
         assert np.isfinite(f[0]).all() and float(np.abs(f[2]).max() + np.abs(f[3]).max()) > 0
         c.residual(L.RES_VELSUM)
         c.get_populations()
+        tally(c, f"{sname} {name}")
         c.close()
         print("ok single", sname, name, n, "f64" if prec == L.F64 else "f32", flush=True)
 
@@ -70,7 +86,8 @@ def slabs(quick):
             for c in cs:
                 f = c.get_fields()
                 assert np.isfinite(f[0]).all()
-            for c in cs:
+            for r, c in enumerate(cs):
+                tally(c, f"slab {r} of {P} storage {st} {name}")
                 c.close()
             print("ok slabs", st, name, P, flush=True)
 
@@ -79,4 +96,5 @@ if __name__ == "__main__":
     q = len(sys.argv) > 1 and sys.argv[1] == "quick"
     single(q)
     slabs(q)
-    print("sanitize_cases done")
+    print(f"sanitize_cases done: out_of_range={TOTAL[0]} touched_by_two_threads={TOTAL[1]} launches_checked={TOTAL[2]}")
+    sys.exit(1 if TOTAL[0] or TOTAL[1] else 0)

@@ -46,8 +46,9 @@ def main():
     rr2 = ((xx % pitch - pitch / 2) ** 2 + (zz % pitch - pitch / 2) ** 2) / (a.radius_frac * pitch) ** 2
     inlet = (0.05 * np.clip(1 - rr2, 0, None)).astype(np.float32)
     out = {}
-    for name, storage in (("dense_ab", L.STORE_DENSE_AB), ("dense_aa", L.STORE_DENSE_AA), ("sparse_ab", L.STORE_SPARSE_AB)):
-        if a.only and name != a.only:
+    for name, storage in (("dense_ab", L.STORE_DENSE_AB), ("dense_aa", L.STORE_DENSE_AA), ("sparse_ab", L.STORE_SPARSE_AB),
+                          ("sparse_aa", L.STORE_SPARSE_AA)):
+        if a.only and name not in a.only.split(","):
             continue
         d = L.case_defaults(L.CASE_GEO_Y_INOUT)
         d.nx = d.ny = d.nz = n
@@ -75,6 +76,14 @@ def main():
         out[name]["checksum_uy"] = float(np.abs(fields[2].astype(np.float64)).sum())
         c.close()
     out["same_fields"] = len({v["checksum_uy"] for v in out.values()}) == 1
+    peak = 6549.1
+    try:
+        peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        pass
+    for v in list(out.values()):
+        if isinstance(v, dict):
+            v["frac_of_measured_peak"] = v["algorithmic_GBps"] / peak
     print(json.dumps(out, indent=1))
 
 

@@ -38,7 +38,7 @@ def desc_for(a, z_range, device):
     d.nx = d.ny = d.nz = a.n
     d.z_begin, d.z_end = z_range
     d.precision = L.F64 if a.precision == "f64" else L.F32
-    d.storage = {"sparse": L.STORE_SPARSE_AB, "dense": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[a.storage]
+    d.storage = {"sparse": L.STORE_SPARSE_AB, "dense": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA}[a.storage]
     d.pulse_amp, d.pulse_period = 0.3, 200.0
     d.bc[0].pulsatile = 1
     d.device = device
