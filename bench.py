@@ -28,8 +28,9 @@ Algorithmic traffic: 2 x 19 x sizeof(real) bytes per fluid-node update (SURVEY 8
 
 --impl reference times the CPU restatement of the reference's loop (oracle/, all host threads)
 on a bounded sample of the same workload; the reference itself is a CUDA program with the grid
-size compiled in (64^3, fp32), so its own binary (oracle/_ref/ldc_ref) is reported separately
-under "reference_cuda" when present.
+size compiled in (64^3, fp32), so its kernels are reported separately under "reference_cuda": a
+patched-constant 480^3 build (baseline/_ref/variants, tools/make_reference_variants.py), with and
+without the per-kernel syncs and the thrust::reduce of its loop.
 """
 import argparse
 import json
@@ -150,27 +151,30 @@ def cpu_oracle_mlups(n, precision, steps, threads):
 
 
 def reference_cuda_line():
-    """MLUPS of the unmodified reference program on this GPU (64^3 fp32, its own cudaEvent span,
-    residual reduce + per-kernel syncs + VTK dumps included: that IS the reference's loop)."""
-    exe = ROOT / "oracle" / "_ref" / "ldc_ref"
-    if not exe.exists():
-        return None
+    """The reference's own kernels on this GPU: ldc.cu with NX=NY=NZ=480 -- the largest cube its
+    32-bit indexing allows (ldc.cu:80) -- fp32, 30 iterations, timed by the program's own cudaEvent span, (a) as
+    shipped: a cudaDeviceSynchronize after each of its three kernels plus a thrust::reduce per step
+    (ldc.cu:655-662), (b) kernels only.  Patched-constant builds from tools/make_reference_variants.py (only the
+    grid constants and the loop's sync / reduce lines are edited, `update` and `boundary_stream` are untouched)."""
+    var = ROOT / "baseline" / "_ref" / "variants"
+    out = {"program": "Lid_driven_cavity/ldc.cu, NX=NY=NZ=480 patched in (nvcc -O3 sm_100a), fp32, 30 iterations, own cudaEvent span"}
     import tempfile
 
-    try:
-        with tempfile.TemporaryDirectory() as wd:
-            os.makedirs(os.path.join(wd, "out"))
-            r = subprocess.run([str(exe)], cwd=wd, capture_output=True, text=True, timeout=300)
-            m = re.search(r"TOTAL RUNNING TIME: ([0-9.eE+-]+) MILLI", r.stdout)
-            its = [int(v) for v in re.findall(r"lid_(\d+)\.vtk", " ".join(os.listdir(os.path.join(wd, "out"))))]
-            if not m or not its:
-                return None
-            ms, k = float(m.group(1)), max(its)
-            return {"program": "Lid_driven_cavity/ldc.cu (unmodified, nvcc sm_100a)", "grid": "64^3 fp32",
-                    "iterations": k, "total_ms": ms, "mlups_fluid": 60 ** 3 * k / (ms * 1e-3) / 1e6,
-                    "mlups_all_nodes": 64 ** 3 * k / (ms * 1e-3) / 1e6}
-    except Exception as e:  # noqa: BLE001
-        return {"error": str(e)[:200]}
+    for key, exe in (("as_shipped_loop", var / "ldc_480"), ("kernels_only", var / "ldc_480_stripped")):
+        if not exe.exists():
+            continue
+        try:
+            with tempfile.TemporaryDirectory() as wd:
+                os.makedirs(os.path.join(wd, "out"))
+                r = subprocess.run([str(exe)], cwd=wd, capture_output=True, text=True, timeout=300)
+                m = re.search(r"TOTAL RUNNING TIME: ([0-9.eE+-]+) MILLI", r.stdout)
+                if m:
+                    ms = float(m.group(1)) / 30
+                    out[key] = {"ms_per_step": ms, "mlups_fluid": 476 ** 3 / (ms * 1e-3) / 1e6,
+                                "GBps_at_152B_per_update": 476 ** 3 * 152 / (ms * 1e-3) / 1e9}
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": str(e)[:200]}
+    return out if len(out) > 1 else None
 
 
 def run_reference_arm(args):
@@ -233,14 +237,8 @@ def bind_to_gpu_numa_node(local):
     try:
         import torch
 
-        bdf = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
-        if bdf is None:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
-                                 capture_output=True, text=True, timeout=10).stdout.strip()
-            bdf = out
-        bdf = bdf.lower()
-        if len(bdf.split(":")[0]) == 8:
-            bdf = bdf[4:]
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
         if node < 0:
             return None
@@ -478,6 +476,8 @@ def run_ours(args):
         barrier()
         t_e2e = time.perf_counter() - t0
         phases = {"setup_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": time.perf_counter() - t2, "numa_node": numa}
+        if getattr(c, "timing", None):
+            phases["setup_breakdown_s"] = {k: round(v, 4) for k, v in c.timing.items()}
         if world > 1:
             t_ = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)

@@ -36,6 +36,7 @@ int main(int argc, char **argv) {
     lbm_handle h = NULL;
     int repeat = 4400, time_save = 4400; /* REPEAT, time_save: bif:19 */
     lbm_case_defaults(LBM_CASE_GEO_Y_INOUT, &d);
+    d.storage = LBM_STORE_SPARSE_AA; /* --storage overrides */
     if (parse_common(argc, argv, &d, &repeat, &time_save)) return 2;
     CHECK(h, lbm_create(&d, &h));
     CHECK(h, lbm_set_output_format(h, g_out_format));

@@ -19,7 +19,8 @@
     } while (0)
 
 /* optional overrides; the reference has none (argc/argv unused, ldc.cu:612):
- *   --n N | --dims NX NY NZ | --f64 | --strict | --steps K | --save S | --tau T | --out DIR | --device D */
+ *   --n N | --dims NX NY NZ | --f64 | --strict | --steps K | --save S | --tau T | --out DIR | --device D
+ *   --storage ab|aa|sparse|sparse_aa   (default of the drivers: sparse_aa, one population buffer over the fluid nodes) */
 static int g_out_format = LBM_OUT_ASCII_VTK; /* --binary: legacy-VTK BINARY dumps instead of the reference's ASCII */
 static int parse_common(int argc, char **argv, lbm_case_desc *d, int *steps, int *save) {
     for (int i = 1; i < argc; i++) {
@@ -32,6 +33,11 @@ static int parse_common(int argc, char **argv, lbm_case_desc *d, int *steps, int
         } else if (!strcmp(argv[i], "--f64")) d->precision = LBM_F64;
         else if (!strcmp(argv[i], "--strict")) d->math = LBM_MATH_STRICT;
         else if (!strcmp(argv[i], "--binary")) g_out_format = LBM_OUT_BINARY_VTK;
+        else if (!strcmp(argv[i], "--storage") && i + 1 < argc) {
+            const char *v = argv[++i];
+            d->storage = !strcmp(v, "ab") ? LBM_STORE_DENSE_AB : !strcmp(v, "aa") ? LBM_STORE_DENSE_AA
+                         : !strcmp(v, "sparse") ? LBM_STORE_SPARSE_AB : LBM_STORE_SPARSE_AA;
+        }
         else if (!strcmp(argv[i], "--steps") && i + 1 < argc) *steps = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--save") && i + 1 < argc) *save = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--tau") && i + 1 < argc) d->tau = atof(argv[++i]);

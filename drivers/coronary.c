@@ -7,6 +7,7 @@ int main(int argc, char **argv) {
     lbm_handle h = NULL;
     int repeat = 300000, time_save = 5000; /* cor:19 */
     lbm_case_defaults(LBM_CASE_GEO_OPENINGS, &d);
+    d.storage = LBM_STORE_SPARSE_AA; /* --storage overrides */
     if (parse_common(argc, argv, &d, &repeat, &time_save)) return 2;
     CHECK(h, lbm_create(&d, &h));
     CHECK(h, lbm_set_output_format(h, g_out_format));

@@ -6,6 +6,7 @@ int main(int argc, char **argv) {
     lbm_handle h = NULL;
     int max_it = 10000, time_save = 500; /* pos:944 */
     lbm_case_defaults(LBM_CASE_POISEUILLE, &d);
+    d.storage = LBM_STORE_SPARSE_AA; /* --storage overrides */
     if (parse_common(argc, argv, &d, &max_it, &time_save)) return 2;
     CHECK(h, lbm_create(&d, &h));
     CHECK(h, lbm_set_output_format(h, g_out_format));

@@ -328,6 +328,11 @@ int lbm_group_run_fixed(lbm_group g, int32_t repeat, int32_t time_save, int32_t 
 int lbm_group_run_converge(lbm_group g, int32_t max_it, double tol, int32_t stag_max, int32_t time_save,
                            int32_t write_files, int32_t *iterations, double *residual);
 
+/* Tuning knobs that are not part of a case description.  "persistent": 1 / 0 forces / forbids the persistent
+ * multi-step kernel of the in-place sparse storage (one cooperative launch for a whole batch of steps, grid
+ * barrier between steps; chosen automatically when the populations fit in L2), -1 restores the automatic choice. */
+int lbm_set_option(lbm_handle h, const char *name, double value);
+
 /* Self-checking build of the library (-DLBM_SELFCHECK; tools/selfcheck.py builds and runs it -- the stand-in for
  * compute-sanitizer, which the GPU pool does not offer): out[0] = population accesses of the step kernels that
  * fell outside the handle's buffers, out[1] = buffer elements touched by two different threads within one launch

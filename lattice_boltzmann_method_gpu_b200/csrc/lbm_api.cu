@@ -86,6 +86,7 @@ struct SolverBase {
     virtual int sync() = 0;
     virtual void *stream_ptr() = 0;
     virtual int selfcheck(uint64_t *out2) = 0;
+    virtual int set_option(const char *name, double value) = 0;
     int64_t steps = 0, launches = 0, nfluid = 0, dev_bytes = 0;
 };
 
@@ -175,6 +176,7 @@ struct Solver final : SolverBase {
     long long face_id0[2] = {0, 0}, face_n[2] = {0, 0};   // compact range of the outermost owned plane per side
 
     ~Solver() override {
+        if (writer.joinable()) writer.join();
         cudaSetDevice(d.device);
         auto fr = [](void *p) {
             if (p) cudaFree(p);
@@ -184,7 +186,7 @@ struct Solver final : SolverBase {
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
         fr(d_sid), fr(d_cmeta);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
-        fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count);
+        fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count), fr(d_pulse), fr(d_barrier);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto &e : ev_face)
@@ -365,6 +367,7 @@ struct Solver final : SolverBase {
         CK(cudaMemcpyAsync(&c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         stored_own = c;
+        join_writer();
         if (have_init && sparse) release_geometry_sized();
         have_geo = true, have_index = false, have_init = false, have_moments = false;
         w_index.clear(), w_rho.clear(), w_ux.clear(), w_uy.clear(), w_uz.clear();  // host mirrors of the old tables
@@ -756,6 +759,59 @@ struct Solver final : SolverBase {
     }
     long long plane_c(int z_global) const { return (long long)(z_global - box.z0) * box.plane; }
 
+    // ---- persistent multi-step launches for grids that live in L2 (step_sparse_aa.cuh, k_sparse_aa_persist)
+    T *d_pulse = nullptr;
+    size_t pulse_cap = 0;
+    unsigned *d_barrier = nullptr;
+    int sm_count = 0;
+    static constexpr int PERSIST_MAX_STEPS = 2048;
+    int opt_persist = -1;  // lbm_set_option("persistent", 0 / 1); -1: by size
+    bool use_persist() {
+        if (d.storage != LBM_STORE_SPARSE_AA || lo_halo || hi_halo) return false;
+#ifdef LBM_SELFCHECK
+        return false;  // the shadow tags are per launch: a launch must be one step
+#endif
+        if (opt_persist >= 0) return opt_persist != 0;
+        // one buffer of 19 directions; below ~half the 126 MB L2 every step is served from L2
+        return (size_t)qstride * Q * sizeof(T) <= (size_t)64 << 20;
+    }
+    // n <= PERSIST_MAX_STEPS steps in one cooperative launch; S_dev: n device slots receiving sum|u| per step, or null
+    int persist_steps(int n, bool moments_last, double *S_dev) {
+        if (n <= 0) return 0;
+        if (!sm_count) {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, d.device));
+            sm_count = prop.multiProcessorCount;
+            CK(cudaMalloc((void **)&d_barrier, sizeof(unsigned)));
+        }
+        const T *pulse_dev = nullptr;
+        if (d.pulse_amp != 0.0) {  // the same scale the single launches get, step by step (make_params)
+            std::vector<T> tab((size_t)n);
+            for (int k = 0; k < n; k++) tab[(size_t)k] = (T)(1.0 + d.pulse_amp * std::sin(2.0 * M_PI * (double)(steps + k) / d.pulse_period));
+            if ((size_t)n > pulse_cap) {
+                if (d_pulse) cudaFree(d_pulse), d_pulse = nullptr;
+                pulse_cap = (size_t)std::max(n, 256);
+                CK(cudaMalloc((void **)&d_pulse, pulse_cap * sizeof(T)));
+            }
+            CK(cudaMemcpyAsync(d_pulse, tab.data(), (size_t)n * sizeof(T), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));  // `tab` is pageable and goes out of scope
+            pulse_dev = d_pulse;
+        }
+        CK(cudaMemsetAsync(d_barrier, 0, sizeof(unsigned), st));
+        SparseParams<T> sp{};
+        sp.base = make_params(plane_c(own_z0), plane_c(own_z1), nullptr);
+        sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc, sp.spw = 1, sp.cartc = d_cart, sp.cmeta = d_cmeta;
+        sp.seg_begin = seg_plane_start[0], sp.seg_end = seg_plane_start[(size_t)(own_z1 - own_z0)];
+        sp.id_begin = own_id0, sp.id_end = own_id1;
+        sp.halo_lo_n = 0, sp.halo_hi0 = INT32_MAX;
+        const int parity0 = (int)(steps & 1);
+        if (d.math == LBM_MATH_STRICT) CK(launch_sparse_aa_persist_strict<T>(sp, n, parity0, moments_last ? 1 : 0, S_dev, pulse_dev, d_barrier, sm_count, st));
+        else CK(launch_sparse_aa_persist_fast<T>(sp, n, parity0, moments_last ? 1 : 0, S_dev, pulse_dev, d_barrier, sm_count, st));
+        launches++;
+        steps += n;
+        return 0;
+    }
+
     // single-domain step loop
     int step(int n, float *ms) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "step before initialize");
@@ -763,11 +819,19 @@ struct Solver final : SolverBase {
         if (n < 0) FAIL(LBM_ERR_ARG, "negative step count");
         CK(cudaSetDevice(d.device));
         if (ms) CK(cudaEventRecord(ev0, st));
-        for (int i = 0; i < n; i++) {
-            int r = launch_range(plane_c(own_z0), plane_c(own_z1), i == n - 1, false, nullptr);
-            if (r) return r;
-            std::swap(d_cur, d_nxt);
-            steps++;
+        if (use_persist()) {
+            for (int done = 0; done < n; done += PERSIST_MAX_STEPS) {
+                const int nb = std::min(PERSIST_MAX_STEPS, n - done);
+                int r = persist_steps(nb, done + nb == n, nullptr);
+                if (r) return r;
+            }
+        } else {
+            for (int i = 0; i < n; i++) {
+                int r = launch_range(plane_c(own_z0), plane_c(own_z1), i == n - 1, false, nullptr);
+                if (r) return r;
+                std::swap(d_cur, d_nxt);
+                steps++;
+            }
         }
         if (n > 0) have_moments = true;
         if (ms) {
@@ -1399,8 +1463,9 @@ struct Solver final : SolverBase {
     }
 
     int output_save(int t) override {
-        int r = fetch_for_output();
+        int r = join_writer();
         if (r) return r;
+        if ((r = fetch_for_output())) return r;
         if (out_format == LBM_OUT_BINARY_VTK) return output_save_binary(t);
         return write_ascii(t);
     }
@@ -1409,6 +1474,8 @@ struct Solver final : SolverBase {
     // handle formats them -- same code as the single-domain writer
     int write_global(int t, const int32_t *index_global, const void *rho, const void *ux, const void *uy, const void *uz,
                      int64_t nlattice) override {
+        int jr = join_writer();
+        if (jr) return jr;
         std::vector<int32_t> si;
         std::vector<T> sr, sx, sy, sz;
         si.swap(w_index), sr.swap(w_rho), sx.swap(w_ux), sy.swap(w_uy), sz.swap(w_uz);
@@ -1420,13 +1487,18 @@ struct Solver final : SolverBase {
         si.swap(w_index), sr.swap(w_rho), sx.swap(w_ux), sy.swap(w_uy), sz.swap(w_uz);
         return r;
     }
-    int write_ascii(int t) {
+    int write_ascii(int t) { return write_ascii_from(t, w_rho.data(), w_ux.data(), w_uy.data(), w_uz.data(), err); }
+    // formats and writes one file from host arrays; touches no other member that a running time loop changes
+    int write_ascii_from(int t, const T *prho, const T *pux, const T *puy, const T *puz, std::string &errout) {
         const int NX = d.nx, NY = d.ny, NZ = d.nz;
         const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
         const float C_pre = C_rho * C_U * C_U;
         std::string path = std::string(d.out_dir) + "/" + d.out_name + "_" + std::to_string(t) + ".vtk";
         std::ofstream ofs(path);
-        if (!ofs) FAIL(LBM_ERR_IO, "cannot write '%s'", path.c_str());
+        if (!ofs) {
+            errout = fmt("cannot write '%s'", path.c_str());
+            return LBM_ERR_IO;
+        }
         using std::endl;
         ofs << "# vtk DataFile Version 2.0" << endl;
         ofs << "<-- LBM flow with UIV acceleration, http://www.bg.ic.ac.uk/research/m.tang/ulis/ -->" << endl;
@@ -1459,12 +1531,12 @@ struct Solver final : SolverBase {
                     for (int y = y0; y < y1; y++)
                         for (int x = x0; x < x1; x++) {
                             const int i = idx_of(x, y, z);
-                            if (kind == 0) put(buf, i >= 0 ? (float)w_rho[i] * C_rho : 0.0f);
+                            if (kind == 0) put(buf, i >= 0 ? (float)prho[i] * C_rho : 0.0f);
                             else if (kind == 1) {
-                                if (i >= 0) put(buf, (float)w_rho[i] * C_pre / 3.0);  // double, as in cor.cu:983
+                                if (i >= 0) put(buf, (float)prho[i] * C_pre / 3.0);  // double, as in cor.cu:983
                                 else put(buf, 0.0f);
                             } else if (i >= 0) {
-                                put(buf, (float)w_ux[i] * C_U), put(buf, (float)w_uy[i] * C_U), put(buf, (float)w_uz[i] * C_U);
+                                put(buf, (float)pux[i] * C_U), put(buf, (float)puy[i] * C_U), put(buf, (float)puz[i] * C_U);
                             } else {
                                 buf += "0 0 0 ";
                             }
@@ -1492,6 +1564,28 @@ struct Solver final : SolverBase {
         return 0;
     }
 
+    // ---- periodic dumps of the run loops are formatted and written by a helper thread while the GPU
+    // keeps stepping (at 64^3 one ASCII dump costs as much host time as ~2000 steps of device time)
+    std::thread writer;
+    std::vector<T> a_rho, a_ux, a_uy, a_uz;  // the snapshot the helper thread reads
+    int writer_rc = 0;
+    std::string writer_err;
+    int join_writer() {
+        if (writer.joinable()) writer.join();
+        const int rc = writer_rc;
+        writer_rc = 0;
+        if (rc) err = writer_err;
+        return rc;
+    }
+    // w_rho .. w_uz were just fetched (fetch_for_output)
+    int save_fetched_async(int t) {
+        if (out_format != LBM_OUT_ASCII_VTK) return output_save_binary(t);
+        int r = join_writer();  // at most one dump in flight
+        if (r) return r;
+        a_rho = w_rho, a_ux = w_ux, a_uy = w_uy, a_uz = w_uz;
+        writer = std::thread([this, t]() { writer_rc = write_ascii_from(t, a_rho.data(), a_ux.data(), a_uy.data(), a_uz.data(), writer_err); });
+        return 0;
+    }
     // write_once(): cor.cu:1033-1051 -- "x,y,z,ux,uy,uz" of every inlet / outlet node (labels 2,3,5,6,7), %f.
     // (coronary.cu defines it but never calls it; the reference's h_u* of those nodes are whatever the
     // device buffers held, here they are 0: nothing ever writes moments of non-fluid nodes.)
@@ -1564,10 +1658,14 @@ struct Solver final : SolverBase {
                     logfile << residual << std::endl;
                     std::cout << "ITERATION # " << upto << ", collapse time: " << milli << " ms, residual:" << residual
                               << std::endl;
-                    r = output_save(upto);
+                    r = save_fetched_async(upto);  // the fields were fetched just above
                     if (r) return r;
                 }
             }
+        }
+        {
+            int r = join_writer();
+            if (r) return r;
         }
         float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (write_files) {
@@ -1609,11 +1707,16 @@ struct Solver final : SolverBase {
                     break;
                 }
             CK(cudaMemsetAsync(d_acc + 2, 0, sizeof(double) * nb, st));
-            for (int j = 0; j < nb; j++) {
-                int r = launch_range(plane_c(own_z0), plane_c(own_z1), true, true, d_acc + 2 + j);
+            if (use_persist()) {  // the whole batch in one cooperative launch; moments of its last step (a save iteration, if any)
+                int r = persist_steps(nb, true, d_acc + 2);
                 if (r) return r;
-                std::swap(d_cur, d_nxt);
-                steps++;
+            } else {
+                for (int j = 0; j < nb; j++) {
+                    int r = launch_range(plane_c(own_z0), plane_c(own_z1), true, true, d_acc + 2 + j);
+                    if (r) return r;
+                    std::swap(d_cur, d_nxt);
+                    steps++;
+                }
             }
             have_moments = true;
             CK(cudaMemcpyAsync(S.data(), d_acc + 2, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
@@ -1626,7 +1729,8 @@ struct Solver final : SolverBase {
                     std::cout << "ITERATION # " << k << ", collapse time: " << milli << " ms, residual:" << residual
                               << std::endl;
                     logfile << residual << std::endl;
-                    int r = output_save(k);
+                    int r = fetch_for_output();
+                    if (!r) r = save_fetched_async(k);
                     if (r) return r;
                 }
                 k++;
@@ -1637,7 +1741,7 @@ struct Solver final : SolverBase {
         }
         float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (write_files) {
-            int r = output_save(k);
+            int r = output_save(k);  // joins the dump in flight first
             if (r) return r;
             std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << std::endl;
             std::cout << "Residual is " << residual << std::endl;
@@ -1672,6 +1776,11 @@ struct Solver final : SolverBase {
             CK(cudaMemset(d_chk_shadow[b], 0, elems * sizeof(unsigned long long)));
         }
         chk_elems = elems;
+        return 0;
+    }
+    int set_option(const char *name, double value) override {
+        if (!strcmp(name, "persistent")) opt_persist = value < 0 ? -1 : (value != 0.0);
+        else FAIL(LBM_ERR_ARG, "unknown option '%s'", name);
         return 0;
     }
     int selfcheck(uint64_t *out2) override {
@@ -1921,6 +2030,7 @@ int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *b
     return h->s->sync_export(handle, ptr, byte_offset);
 }
 int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync) { H_OR_FAIL; return h->s->sync_attach(side, peer_sync); }
+int lbm_set_option(lbm_handle h, const char *name, double value) { H_OR_FAIL; return name ? h->s->set_option(name, value) : LBM_ERR_ARG; }
 int lbm_debug_selfcheck(lbm_handle h, uint64_t out[3]) { H_OR_FAIL; return out ? h->s->selfcheck(out) : LBM_ERR_ARG; }
 int lbm_write_bc_csv(lbm_handle h, const char *path) { H_OR_FAIL; return path ? h->s->write_bc_csv(path) : LBM_ERR_ARG; }
 

@@ -217,6 +217,13 @@ template <typename T>
 cudaError_t launch_step_sparse_aa_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_sparse_aa_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
+// nsteps steps of a single-domain in-place sparse handle in ONE cooperative launch (grids that live in L2)
+template <typename T>
+cudaError_t launch_sparse_aa_persist_fast(const SparseParams<T> &p, int nsteps, int parity0, int moments_last, double *S,
+                                          const T *pulse, unsigned *barrier, int sm_count, cudaStream_t s);
+template <typename T>
+cudaError_t launch_sparse_aa_persist_strict(const SparseParams<T> &p, int nsteps, int parity0, int moments_last, double *S,
+                                            const T *pulse, unsigned *barrier, int sm_count, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_dense_fast(const StepParams<T> &p, bool moments, bool resid, int storage, cudaStream_t s);
 template <typename T>

@@ -29,4 +29,14 @@ cudaError_t launch_step_sparse_aa_fast(const SparseParams<T> &p, bool moments, b
 }
 template cudaError_t launch_step_sparse_aa_fast<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
 template cudaError_t launch_step_sparse_aa_fast<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+template <typename T>
+cudaError_t launch_sparse_aa_persist_fast(const SparseParams<T> &p, int nsteps, int parity0, int moments_last, double *S,
+                                             const T *pulse, unsigned *barrier, int sm_count, cudaStream_t s) {
+    PersistArgs<T> a{nsteps, parity0, moments_last, S ? 1 : 0, S, pulse, barrier};
+    return launch_sparse_aa_persist_impl<T, false>(p, a, sm_count, s);
+}
+template cudaError_t launch_sparse_aa_persist_fast<float>(const SparseParams<float> &, int, int, int, double *, const float *,
+                                                             unsigned *, int, cudaStream_t);
+template cudaError_t launch_sparse_aa_persist_fast<double>(const SparseParams<double> &, int, int, int, double *, const double *,
+                                                              unsigned *, int, cudaStream_t);
 }  // namespace lbm

@@ -33,4 +33,14 @@ cudaError_t launch_step_sparse_aa_strict(const SparseParams<T> &p, bool moments,
 }
 template cudaError_t launch_step_sparse_aa_strict<float>(const SparseParams<float> &, bool, bool, cudaStream_t);
 template cudaError_t launch_step_sparse_aa_strict<double>(const SparseParams<double> &, bool, bool, cudaStream_t);
+template <typename T>
+cudaError_t launch_sparse_aa_persist_strict(const SparseParams<T> &p, int nsteps, int parity0, int moments_last, double *S,
+                                             const T *pulse, unsigned *barrier, int sm_count, cudaStream_t s) {
+    PersistArgs<T> a{nsteps, parity0, moments_last, S ? 1 : 0, S, pulse, barrier};
+    return launch_sparse_aa_persist_impl<T, true>(p, a, sm_count, s);
+}
+template cudaError_t launch_sparse_aa_persist_strict<float>(const SparseParams<float> &, int, int, int, double *, const float *,
+                                                             unsigned *, int, cudaStream_t);
+template cudaError_t launch_sparse_aa_persist_strict<double>(const SparseParams<double> &, int, int, int, double *, const double *,
+                                                              unsigned *, int, cudaStream_t);
 }  // namespace lbm

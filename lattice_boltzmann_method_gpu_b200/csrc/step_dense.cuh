@@ -69,7 +69,7 @@ __device__ __noinline__ void chk_touch(const StepParams<T> &p, const T *a, bool 
 
 // prescribed boundary speed of BC entry `e` at boundary node (gx, gy, gz) (global coords)
 template <typename T>
-__device__ __forceinline__ T bc_speed(const StepParams<T> &p, const BcEntry &e, int gx, int gz) {
+__device__ __forceinline__ T bc_speed(const StepParams<T> &p, const BcEntry &e, int gx, int gz, T pulse) {
     T u;
     if (e.source == LBM_SRC_CONST) {
         u = (T)e.value;
@@ -84,7 +84,7 @@ __device__ __forceinline__ T bc_speed(const StepParams<T> &p, const BcEntry &e, 
     } else {
         u = p.plane_out[gx + (long long)gz * p.box.nx];
     }
-    if (e.pulsatile) u = u * p.pulse_scale;
+    if (e.pulsatile) u = u * pulse;
     return u;
 }
 
@@ -122,7 +122,7 @@ enum { MODE_AB = 0, MODE_AA_EVEN = 1, MODE_AA_ODD = 2 };
 // few nodes set the lifetime of their CTA, which is what a small grid's step time consists of.
 template <typename T>
 __device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long c, uint32_t rest, int mode, T rho, T ux,
-                                               T uy, T uz, const T *g, const T *fpre, T *out) {
+                                               T uy, T uz, const T *g, const T *fpre, T *out, T pulse) {
     const Box &b = p.box;
     int x, y, zl;  // coordinates of the node, once (32-bit arithmetic when the cell id allows it)
     if (c < 0x7fffffffLL) {
@@ -148,7 +148,7 @@ __device__ __noinline__ uint32_t boundary_node(const StepParams<T> &p, long long
             caxis(q, p.bc[l].naxis) == p.bc[l].nsign) {
             bcm |= 1u << q;
             // the speed is sampled at the boundary node s = x - c_q itself (pos.cu:597)
-            if (p.bc[l].kind != LBM_BC_P) ubc[q] = bc_speed<T>(p, p.bc[l], x - cxq(q), zl - czq(q) + b.z0);
+            if (p.bc[l].kind != LBM_BC_P) ubc[q] = bc_speed<T>(p, p.bc[l], x - cxq(q), zl - czq(q) + b.z0, pulse);
         }
     }
     const T r3 = rho / T(3.0), r18 = rho / T(18.0), r36 = rho / T(36.0);
@@ -352,7 +352,7 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
 #pragma unroll
                 for (int q = 0; q < Q; q++) fpre[q] = T(0.0);
             }
-            const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, fpre, hv);
+            const uint32_t wm = boundary_node<T>(p, (long long)c, rest, MODE, rho, ux, uy, uz, gl, fpre, hv, p.pulse_scale);
 #pragma unroll
             for (int q = 1; q < Q; q++) {
                 if (wm & (1u << q)) {

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SP64_MINB :
                     T gl[Q], hv[Q];
 #pragma unroll
                     for (int q = 0; q < Q; q++) gl[q] = f[q];
-                    const uint32_t wm = boundary_node<T>(p, c, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv);
+                    const uint32_t wm = boundary_node<T>(p, c, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv, p.pulse_scale);
 #pragma unroll
                     for (int q = 1; q < Q; q++)
                         if (wm & (1u << q)) {

@@ -36,10 +36,10 @@ namespace lbm {
 #define LBM_SPAA32_MINB 10
 #endif
 #ifndef LBM_SPAA64_ODD_MINB
-#define LBM_SPAA64_ODD_MINB 6
+#define LBM_SPAA64_ODD_MINB 5  // 96 registers, no spills: +1.2 % over 6 x 80 with 22 spilled words
 #endif
 #ifndef LBM_SPAA32_ODD_MINB
-#define LBM_SPAA32_ODD_MINB 10
+#define LBM_SPAA32_ODD_MINB 8  // 64 registers: +12 % over 10 x 48 with 43 spilled words
 #endif
 
 // neighbouring rows (c_y, c_z) != (0,0) of D3Q19 and the direction with c_x = 0 in each
@@ -52,15 +52,22 @@ __host__ __device__ constexpr int row_of(int k) {
     return a[k];
 }
 
+// population load: plain, or (persistent kernel, where other SMs rewrote the element since this SM last
+// read it and no kernel boundary has invalidated L1 in between) served by L2
+template <bool CG, typename T>
+__device__ __forceinline__ T ld_pop(const T *a) {
+    return CG ? __ldcg(a) : *a;
+}
+
 // inlet / outlet links of a node, after its collision: the extrapolated value goes into the own slot
 template <typename T>
 __device__ __forceinline__ void own_slot_bc(const StepParams<T> &p, long long cart, long long i, uint32_t rest, T rho, T ux,
-                                            T uy, T uz, const T (&f)[Q]) {
+                                            T uy, T uz, const T (&f)[Q], T pulse) {
     T gl[Q], hv[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) gl[q] = f[q];
     // static links report no value (mode MODE_AB): their slot is left alone
-    const uint32_t wm = boundary_node<T>(p, cart, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv);
+    const uint32_t wm = boundary_node<T>(p, cart, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv, pulse);
 #pragma unroll
     for (int q = 1; q < Q; q++)
         if (wm & (1u << q)) {
@@ -69,63 +76,59 @@ __device__ __forceinline__ void own_slot_bc(const StepParams<T> &p, long long ca
         }
 }
 
-template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
-__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB : LBM_SPAA32_MINB)
-    k_sparse_aa_even(const __grid_constant__ SparseParams<T> sp) {
+// per-step switches that are template parameters of the one-step kernels and run-time values of the
+// persistent one
+struct AaStep {
+    bool moments, resid;
+};
+
+// the local (even) step of one node i in [sp.id_begin, sp.id_end)
+template <typename T, bool STRICT, bool PEERS, bool CG>
+__device__ __forceinline__ void aa_even_node(const SparseParams<T> &sp, long long i, AaStep st, T pulse, double &velsum) {
     const StepParams<T> &p = sp.base;
-    const long long i = sp.id_begin + (long long)blockIdx.x * SPARSE_BLOCK + threadIdx.x;
-    double velsum = 0.0;
     // one word per 32 ids says which lanes are fluid and whether any of them needs its node word at all
     // (walls need nothing in the local step): 0.25 B of metadata per node instead of 4
     uint2 cm = make_uint2(0u, 0u);
     if (i < sp.id_end) cm = sp.cmeta[i >> 5];
-    if ((cm.x >> (i & 31)) & 1u) {
-        T f[Q];
+    if (!((cm.x >> (i & 31)) & 1u)) return;
+    T f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        LBM_CHK(p, p.pull_base[q] + i);
+        f[q] = ld_pop<CG>(p.pull_base[q] + i);
+    }
+    uint32_t node = 0u, rest = 0u;  // rest: links that are neither fluid-fed nor walls: inlet / outlet / static
+    if (cm.y) node = sp.nodec[i];
+    if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
+    T rho, ux, uy, uz;
+    collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+    if (rest == 0u) {
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            LBM_CHK(p, p.pull_base[q] + i);
-            f[q] = p.pull_base[q][i];
+            LBM_CHK(p, p.store_base[q] + i);
+            p.store_base[q][i] = f[oppq(q)];
         }
-        uint32_t node = 0u, rest = 0u;  // rest: links that are neither fluid-fed nor walls: inlet / outlet / static
-        if (cm.y) node = sp.nodec[i];
-        if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
-        T rho, ux, uy, uz;
-        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-        if (rest == 0u) {
+    } else {
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
+        for (int q = 0; q < Q; q++)
+            if (!(rest & (1u << q))) {
                 LBM_CHK(p, p.store_base[q] + i);
                 p.store_base[q][i] = f[oppq(q)];
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < Q; q++)
-                if (!(rest & (1u << q))) {
-                    LBM_CHK(p, p.store_base[q] + i);
-                    p.store_base[q][i] = f[oppq(q)];
-                }
-            if (node & NODE_HAS_BC) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f);
-        }
-        if (MOMENTS) {
-            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
-        }
-        if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
-        if (PEERS) push_to_peers<T, MODE_AA_EVEN>(p, i - p.face_c0, node, f);
+        if (node & NODE_HAS_BC) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f, pulse);
     }
-    if (RESID) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
-        if ((threadIdx.x & 31) == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    if (st.moments) {
+        p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
     }
+    if (st.resid) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+    if (PEERS) push_to_peers<T, MODE_AA_EVEN>(p, i - p.face_c0, node, f);
 }
 
-template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
-__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_MINB : LBM_SPAA32_ODD_MINB)
-    k_sparse_aa_odd(const __grid_constant__ SparseParams<T> sp) {
+// the neighbour (odd) step of one record: a whole warp calls this with the same `seg`
+template <typename T, bool STRICT, bool PEERS, bool CG>
+__device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long long seg, AaStep st, T pulse, double &velsum) {
     const StepParams<T> &p = sp.base;
     const int lane = threadIdx.x & 31;
-    const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
-    if (seg >= sp.seg_end) return;  // warp-uniform
     const int32_t r0 = sp.rec[seg * SEG_REC + lane];
     const int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
     const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
@@ -150,57 +153,155 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_
         const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
         has_links = inB ? bl : has_links;
     }
-    double velsum = 0.0;
-    if (active) {
-        const uint32_t node = has_links ? sp.nodec[i] : 0u;
-        // ONE element index per direction, used for the load and for the store: inside the array of opp(k),
-        // either the source's id or -- for a link -- this node's own slot in the array of k, which lies
-        // dk[k] = (k - opp k) * qstride elements away
-        int idx[Q];
-        T f[Q];
-        LBM_CHK(p, p.pull_base[0] + i);
-        f[0] = p.pull_base[0][i];
+    if (!active) return;
+    const uint32_t node = has_links ? sp.nodec[i] : 0u;
+    // ONE element index per direction, used for the load and for the store: inside the array of opp(k),
+    // either the source's id or -- for a link -- this node's own slot in the array of k, which lies
+    // dk[k] = (k - opp k) * qstride elements away
+    int idx[Q];
+    T f[Q];
+    LBM_CHK(p, p.pull_base[0] + i);
+    f[0] = ld_pop<CG>(p.pull_base[0] + i);
 #pragma unroll
-        for (int k = 1; k < Q; k++) {
-            const int n = (k < 3 ? i : j[row_of(k) < 0 ? 0 : row_of(k)]) - cxq(k);
-            idx[k] = (node & (1u << k)) ? i + sp.dk[k] : n;
-            LBM_CHK(p, p.pull_base[oppq(k)] + idx[k]);
-            f[k] = p.pull_base[oppq(k)][idx[k]];
-        }
-        uint32_t rest = 0u;
-        if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
-        T rho, ux, uy, uz;
-        collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
-        LBM_CHK(p, p.store_base[0] + i);
-        p.store_base[0][i] = f[0];
+    for (int k = 1; k < Q; k++) {
+        const int n = (k < 3 ? i : j[row_of(k) < 0 ? 0 : row_of(k)]) - cxq(k);
+        idx[k] = (node & (1u << k)) ? i + sp.dk[k] : n;
+        LBM_CHK(p, p.pull_base[oppq(k)] + idx[k]);
+        f[k] = ld_pop<CG>(p.pull_base[oppq(k)] + idx[k]);
+    }
+    uint32_t rest = 0u;
+    if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
+    T rho, ux, uy, uz;
+    collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
+    LBM_CHK(p, p.store_base[0] + i);
+    p.store_base[0][i] = f[0];
 #pragma unroll
-        for (int k = 1; k < Q; k++) {
-            if (rest & (1u << k)) continue;  // inlet / outlet (written below) or static (kept) link
-            if (PEERS && !(node & (1u << k))) {
-                if (czq(k) > 0 && p.peer_dn && idx[k] < sp.halo_lo_n) {
-                    // the target x - c_k lies in the low halo plane: it is a node the neighbour below owns
-                    p.peer_dn[(long long)oppq(k) * p.peer_dn_qs + p.peer_dn_own + idx[k]] = f[oppq(k)];
-                    continue;
-                }
-                if (czq(k) < 0 && p.peer_up && idx[k] >= sp.halo_hi0) {
-                    p.peer_up[(long long)oppq(k) * p.peer_up_qs + p.peer_up_own + (idx[k] - sp.halo_hi0)] = f[oppq(k)];
-                    continue;
-                }
+    for (int k = 1; k < Q; k++) {
+        if (rest & (1u << k)) continue;  // inlet / outlet (written below) or static (kept) link
+        if (PEERS && !(node & (1u << k))) {
+            if (czq(k) > 0 && p.peer_dn && idx[k] < sp.halo_lo_n) {
+                // the target x - c_k lies in the low halo plane: it is a node the neighbour below owns
+                p.peer_dn[(long long)oppq(k) * p.peer_dn_qs + p.peer_dn_own + idx[k]] = f[oppq(k)];
+                continue;
             }
-            LBM_CHK(p, p.store_base[oppq(k)] + idx[k]);
-            p.store_base[oppq(k)][idx[k]] = f[oppq(k)];
+            if (czq(k) < 0 && p.peer_up && idx[k] >= sp.halo_hi0) {
+                p.peer_up[(long long)oppq(k) * p.peer_up_qs + p.peer_up_own + (idx[k] - sp.halo_hi0)] = f[oppq(k)];
+                continue;
+            }
         }
-        if (rest && (node & NODE_HAS_BC)) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f);
-        if (MOMENTS) {
-            p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
-        }
-        if (RESID) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+        LBM_CHK(p, p.store_base[oppq(k)] + idx[k]);
+        p.store_base[oppq(k)][idx[k]] = f[oppq(k)];
     }
-    if (RESID) {
+    if (rest && (node & NODE_HAS_BC)) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f, pulse);
+    if (st.moments) {
+        p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
+    }
+    if (st.resid) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
+}
+
+__device__ __forceinline__ void warp_add(double *dst, double v) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
-        if (lane == 0 && velsum != 0.0) atomicAdd(p.resid, velsum);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB : LBM_SPAA32_MINB)
+    k_sparse_aa_even(const __grid_constant__ SparseParams<T> sp) {
+    const long long i = sp.id_begin + (long long)blockIdx.x * SPARSE_BLOCK + threadIdx.x;
+    double velsum = 0.0;
+    aa_even_node<T, STRICT, PEERS, false>(sp, i, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
+    if (RESID) warp_add(sp.base.resid, velsum);
+}
+
+template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
+__global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_MINB : LBM_SPAA32_ODD_MINB)
+    k_sparse_aa_odd(const __grid_constant__ SparseParams<T> sp) {
+    const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
+    if (seg >= sp.seg_end) return;  // warp-uniform
+    double velsum = 0.0;
+    aa_odd_record<T, STRICT, PEERS, false>(sp, seg, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
+    if (RESID) warp_add(sp.base.resid, velsum);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent form for grids that live in L2 (64^3 and the like: the reference's own configurations).
+// There a time step moves a few MB, so a launch per step spends most of its time in launch latency and in
+// the tail of its last wave.  ONE cooperative launch runs `nsteps` steps: every warp walks its share of
+// the chunks (even step) or records (odd step), then all CTAs meet at a grid barrier (one monotonic counter
+// in global memory; co-residency is guaranteed by cudaLaunchCooperativeKernel).  Populations are read with
+// ld.global.cg: between two steps other SMs rewrote them and no kernel boundary invalidated L1.
+// Per-step values that the one-step kernels get as launch parameters come from small tables: the
+// pulsatile inlet scale of step s (computed by the host exactly as for single launches) and the slot S[s]
+// that receives sum|u| of that step.
+template <typename T>
+struct PersistArgs {
+    int nsteps, parity0;
+    int moments_last, resid;
+    double *S;          // [nsteps] when resid
+    const T *pulse;     // [nsteps] or null (scale 1)
+    unsigned *barrier;  // zero at launch
+};
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
     }
+    __syncthreads();
+}
+// Few, large CTAs: the barrier costs one atomic and one polling thread per CTA, all on one L2 line --
+// 1480 CTAs of 128 threads made a step 19 us, one or two CTAs of 512 threads per SM keep it near the L2
+// round trip (profiles/r02_notes.md).
+constexpr int PERSIST_BLOCK = 512;
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
+    k_sparse_aa_persist(const __grid_constant__ SparseParams<T> sp, const __grid_constant__ PersistArgs<T> pa) {
+    const long long warp0 = (long long)blockIdx.x * (PERSIST_BLOCK / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (PERSIST_BLOCK / 32);
+    const int lane = threadIdx.x & 31;
+    const long long first_chunk = sp.id_begin >> 5, end_chunk = (sp.id_end + 31) >> 5;
+    for (int s = 0; s < pa.nsteps; s++) {
+        const AaStep st{pa.moments_last && s == pa.nsteps - 1, pa.resid != 0};
+        const T pulse = pa.pulse ? pa.pulse[s] : T(1.0);
+        double velsum = 0.0;
+        if (((pa.parity0 + s) & 1) == 0) {
+            for (long long c = first_chunk + warp0; c < end_chunk; c += nwarps) {
+                const long long i = c * 32 + lane;
+                if (i >= sp.id_begin) aa_even_node<T, STRICT, false, true>(sp, i, st, pulse, velsum);
+            }
+        } else {
+            for (long long seg = sp.seg_begin + warp0; seg < sp.seg_end; seg += nwarps)
+                aa_odd_record<T, STRICT, false, true>(sp, seg, st, pulse, velsum);
+        }
+        if (st.resid) warp_add(pa.S + s, velsum);
+        if (s + 1 < pa.nsteps) grid_barrier(pa.barrier, (unsigned)(s + 1) * gridDim.x);
+    }
+}
+template <typename T, bool STRICT>
+cudaError_t launch_sparse_aa_persist_impl(const SparseParams<T> &p_in, const PersistArgs<T> &pa, int sm_count, cudaStream_t s) {
+    SparseParams<T> p = p_in;
+    for (int q = 0; q < Q; q++) {
+        p.base.pull_base[q] = p.base.src + (long long)q * p.base.qstride;
+        p.base.store_base[q] = p.base.dst + (long long)q * p.base.qstride;
+        p.dk[q] = (int)((long long)(q - oppq(q)) * p.base.qstride);
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sparse_aa_persist<T, STRICT>, PERSIST_BLOCK, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = std::min(per_sm, sizeof(T) == 8 ? 1 : 2);
+    const long long work = std::max((p.id_end - p.id_begin + 31) / 32 + 1, p.seg_end - p.seg_begin);
+    long long blocks = std::min<long long>((long long)sm_count * per_sm, (work + PERSIST_BLOCK / 32 - 1) / (PERSIST_BLOCK / 32));
+    if (blocks < 1) blocks = 1;
+    PersistArgs<T> a = pa;
+    void *args[2] = {(void *)&p, (void *)&a};
+    return cudaLaunchCooperativeKernel((const void *)k_sparse_aa_persist<T, STRICT>, dim3((unsigned)blocks), dim3(PERSIST_BLOCK), args, 0, s);
 }
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>

@@ -89,6 +89,7 @@ class SlabCase(api.Case):
         self._bufs = None
         self._p2p = False
         self._sync_ptrs = []
+        self.timing = {}         # seconds spent in the phases of setup / enable_p2p (bench.py reports them)
         self._mapped = []        # IPC handles this rank holds a mapping of
         self.p2p_error = None    # why enable_p2p fell back, if it did
 
@@ -97,21 +98,27 @@ class SlabCase(api.Case):
         import torch
         import torch.distributed as dist
 
+        import time
+
+        t0 = time.perf_counter()
         if flag is not None:
             self.set_flag(flag)
         if flag_slab is not None:  # only the planes this rank needs: (uint8 array, z_first)
             self.set_flag_slab(*flag_slab)
         self.geo_pre()
+        t1 = time.perf_counter()
         mine = torch.tensor([self.local_stored_count()], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(allc, mine, group=self.group)
-        offs, total = compact_offsets([int(t.item()) for t in allc])
+        allc = torch.empty(self.world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        offs, total = compact_offsets(allc.cpu().tolist())
+        t2 = time.perf_counter()
         self.set_compact_offset(offs[self.rank], total)
         self.index_transform()
         if bc_planes is not None:
             self.set_bc_planes(*bc_planes)
         self.initialize()
         self._wrap_buffers()
+        self.timing.update(geo_pre=t1 - t0, count_exchange=t2 - t1, index_init=time.perf_counter() - t2)
 
     def enable_p2p(self):
         """Fused halo exchange: every rank maps its neighbours' population buffers and sync blocks (CUDA
@@ -121,6 +128,9 @@ class SlabCase(api.Case):
         import torch
         import torch.distributed as dist
 
+        import time
+
+        t0 = time.perf_counter()
         mine = self.p2p_export()
         mine.pop("ptrs")  # raw pointers mean nothing in another process
         sy = self.sync_export()
@@ -135,6 +145,7 @@ class SlabCase(api.Case):
         allt = torch.empty(self.world * rec.size, dtype=torch.uint8, device="cuda")
         dist.all_gather_into_tensor(allt, t, group=self.group)
         allr = allt.cpu().numpy().reshape(self.world, rec.size)
+        t1 = time.perf_counter()
         ok, attached = 1, []
         try:
             for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
@@ -160,9 +171,11 @@ class SlabCase(api.Case):
                 self.p2p_attach(side, None, None)
             self._release_mappings()
             return False
+        t2 = time.perf_counter()
         self._sync_ptrs = attached
         self._attach_sync()
         self._p2p = True
+        self.timing.update(handle_exchange=t1 - t0, ipc_open=t2 - t1, sync_attach=time.perf_counter() - t2)
         return True
 
     def _attach_sync(self):

@@ -116,8 +116,14 @@ def test_gpu_reproduces_reference_convergence_runs(name, rule, tol, tmp_path):
     assert len(vtks) in (int(GOLD[f"{name}_n_vtk"]), int(GOLD[f"{name}_n_vtk"]) + 1)
     lines = (tmp_path / f"{prefix}_{its}.vtk").read_text().split("\n")
     assert lines[:9] == [str(s) for s in GOLD[f"{name}_header"]]
-    geo, idx = c.get_geo(), c.get_index()
-    rho, ux, uy, uz = c.get_fields()
+    # fields at the iteration the REFERENCE stopped at (the loop above may stop a few iterations earlier or
+    # later -- its S is an atomic float sum -- and the flow is still evolving there)
+    d.out_dir = str(tmp_path / "unused").encode()
+    e = L.Case(d)
+    e.geo_pre(), e.index_transform(), e.initialize()
+    e.step(ref_its)
+    geo, idx = e.get_geo(), e.get_index()
+    rho, ux, uy, uz = e.get_fields()
     compare(name, vtk_velocity(name, geo.shape, idx, ux, uy, uz), tol)
     log = [float(l) for l in (tmp_path / "CONVERGENCE.log").read_text().split("\n") if l and not l.startswith("TOTAL")]
     ref = GOLD[f"{name}_residuals"]

@@ -189,3 +189,49 @@ def test_sparse_aa_irregular_rows(prec):
             c.step(nsteps)
             for r, g in zip(o.fields(), c.get_fields()):
                 assert np.array_equal(r, g), (c.desc.storage, c.step_count)
+
+
+@pytest.mark.parametrize("name,n", [("ldc", 24), ("bif", None), ("corstep", None)])
+def test_persistent_launches_equal_single_launches(name, n):
+    """small grids run a whole batch of steps in ONE cooperative launch (grid barrier between steps,
+    csrc/step_sparse_aa.cuh k_sparse_aa_persist); same bits as one launch per step, pulsatile table,
+    per-step residual slots and odd batch boundaries included"""
+    L = S()
+    pulse = (0.3, 40.0) if name == "bif" else None
+    runs = []
+    for persistent in (1, 0):
+        c = H.gpu_case(name, n, L.F64, L.MATH_STRICT, storage=L.STORE_SPARSE_AA, pulse=pulse)
+        H.gpu_setup(c, name)
+        c.set_option("persistent", persistent)
+        l0 = c.launch_count
+        for nsteps in (1, 2, 7, 64, 131):
+            c.step(nsteps)
+        runs.append(([a.copy() for a in c.get_fields()], c.launch_count - l0, c.step_count))
+    (fa, la, sa), (fb, lb, sb) = runs
+    assert sa == sb == 205
+    for x, y in zip(fa, fb):
+        assert np.array_equal(x, y)
+    assert la == 5 and lb == 205  # one launch per lbm_step call against one per step
+    o, *_ = H.oracle_case(name, n, np.float64, pulse=pulse)
+    o.step(205)
+    for r, g in zip(o.fields(), fa):
+        assert np.array_equal(r, g)
+    with pytest.raises(L.LbmError):
+        c.set_option("no_such_option", 1)
+
+
+def test_persistent_convergence_loop_stops_on_the_same_iteration():
+    L = S()
+    res = []
+    for persistent in (1, 0):
+        d = L.case_defaults(L.CASE_LDC)
+        d.nx = d.ny = d.nz = 24
+        d.z_begin, d.z_end = 0, 24
+        d.precision, d.storage = L.F64, L.STORE_SPARSE_AA
+        c = L.Case(d)
+        c.geo_pre(), c.index_transform(), c.initialize()
+        c.set_option("persistent", persistent)
+        res.append((c.run_converge(3000, 1e-5, 20, 500, False), c.get_fields()))
+    assert res[0][0] == res[1][0] and res[0][0][0] > 50
+    for x, y in zip(res[0][1], res[1][1]):
+        assert np.array_equal(x, y)

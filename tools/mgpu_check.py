@@ -34,6 +34,8 @@ def main():
         storage = L.STORE_SPARSE_AB if os.environ.get("LBM_SPARSE") == "1" else L.STORE_DENSE_AB
         if os.environ.get("LBM_AA") == "1":  # in-place storage: peer stores are its only transport
             storage = L.STORE_DENSE_AA
+        if os.environ.get("LBM_SPARSE_AA") == "1":
+            storage = L.STORE_SPARSE_AA
         base = H.gpu_case(name, n, L.F64, L.MATH_FAST, z_range=(z0, z1), storage=storage)
         d = base.desc
         d.device = local
@@ -41,9 +43,13 @@ def main():
         c = slab.SlabCase(d)
         flag = H.bif_flag() if name == "bif" else (H.synthetic_openings_mask()[0] if name == "cor" else None)
         c.setup(flag=flag, bc_planes=H.bif_bc_planes() if name == "bif" else None)
-        if os.environ.get("LBM_P2P") == "1" or storage == L.STORE_DENSE_AA:
+        if os.environ.get("LBM_P2P") == "1" or storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
             assert c.enable_p2p(), f"peer mapping unavailable: {c.p2p_error}"
         c.step(steps)
+        if c._p2p and name == "ldc":  # the multi-process convergence loop: S all-reduced per batch (ldc.cu:653-685)
+            its, res = c.run_converge(max_it=steps + 39, tol=0.0, stag_max=10 ** 9, time_save=10 ** 9)
+            assert its == steps + 40, its
+            steps += its
         mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
         counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
         dist.all_gather(counts, torch.tensor([mine[0].numel()], dtype=torch.int64, device="cuda"))
