@@ -256,7 +256,8 @@ def parity_check_single(args, L, prec, local, nfluid_expected):
     """benchmarked kernel (in-place, FAST) vs two-buffer STRICT on the benchmarked box, same step count"""
     n, steps = args.n, args.warmup + args.steps
     fields = {}
-    for name, storage, math in (("bench", {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage], L.MATH_FAST),
+    for name, storage, math in (("bench", {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA,
+                                           "sparse": L.STORE_SPARSE_AB}[args.storage], L.MATH_FAST),
                                 ("strict_ab", L.STORE_DENSE_AB, L.MATH_STRICT)):
         d = L.case_defaults(L.CASE_LDC)
         d.nx = d.ny = d.nz = n
@@ -294,7 +295,7 @@ def parity_check_multi(args, L, slab, prec, rank, world, local):
         flag = np.unpackbits(bits)[: 64 * 83 * 32].astype(np.int32).reshape(32, 83, 64)
         bc = np.load(gold / "bif_bc.npy")
         cases.append(("bifurcation_64x83x32", L.CASE_GEO_Y_INOUT, None, flag, (bc[1], bc[2])))
-    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage]
+    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA, "sparse": L.STORE_SPARSE_AB}[args.storage]
     for name, rule, dims, flag, planes in cases:
         def desc(z0, z1):
             d = L.case_defaults(rule)
@@ -373,7 +374,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.n
     prec = L.F64 if args.precision == "f64" else L.F32
-    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA}[args.storage]
+    storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA, "sparse": L.STORE_SPARSE_AB}[args.storage]
     dtype = np.float64 if args.precision == "f64" else np.float32
 
     gnx, gny, gnz = global_dims(args, world)
@@ -397,12 +398,12 @@ def run_ours(args):
             c.index_transform()
             c.initialize()
             return c
-        if args.halo != "p2p" and storage == L.STORE_DENSE_AA:
-            raise SystemExit("--storage aa exchanges slab faces by peer stores only: use --halo p2p or --storage ab")
+        if args.halo != "p2p" and storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
+            raise SystemExit("in-place storages exchange slab faces by peer stores only: use --halo p2p or --storage ab")
         c.setup()
         if args.halo == "p2p" and not c.enable_p2p():  # the decision is all-reduced: every rank takes the same branch
             args.halo = "nccl (peer mapping unavailable)"
-            if storage == L.STORE_DENSE_AA:
+            if storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
                 c.close()
                 storage, args.storage = L.STORE_DENSE_AB, "ab"
                 c = build_case()
@@ -506,7 +507,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(args.precision, n, args.storage),
                          "peak_source": peak_src,
-                         "kernel": "k_step_dense", "algorithmic_bytes_per_launch": nfluid_local * bpl,
+                         "kernel": "k_step_dense" if args.storage in ("ab", "aa") else ("k_sparse_aa_even / k_sparse_aa_odd" if args.storage == "sparse_aa" else "k_step_sparse"), "algorithmic_bytes_per_launch": nfluid_local * bpl,
                          "frac_of_spec_8TBs": achieved / 8000.0},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_check": parity,
             "wall_ms_per_step": wall / args.steps * 1e3, "fluid_nodes": int(nfluid),
@@ -531,8 +532,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--storage", default="aa", choices=["ab", "aa"],
-                    help="aa: one population buffer streamed in place (default); ab: two buffers")
+    ap.add_argument("--storage", default="aa", choices=["ab", "aa", "sparse_aa", "sparse"],
+                    help="aa: box-dense, one population buffer streamed in place (default); ab: two buffers; "
+                         "sparse_aa: fluid nodes only, one buffer, in place; sparse: reference compact order, two buffers")
     ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
                     help="global box (default n x n x n*gpus, i.e. weak scaling with one n^3 slab per GPU)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],

@@ -17,6 +17,23 @@ __device__ __forceinline__ T parabola_at(const Box &b, T umax, int x, int z) {
     return umax * (T(1.0) - (dx * dx + dz * dz) / (r * r));
 }
 
+// prescribed boundary speed of BC entry `e` at boundary node (gx, ., gz) (global coordinates), before the
+// pulsatile scale: a constant (ldc.cu:378, cor:717), the analytic parabola evaluated at the boundary node's own
+// (i,k) (pos.cu:597; squares of half-integers are exact, so a*a equals the reference's powf(a,2)), or the
+// bc.txt planes (bif:650,951)
+template <typename T>
+__device__ __forceinline__ T bc_speed_unscaled(const BcEntry &e, const Box &b, const T *plane_in, const T *plane_out, int gx,
+                                               int gz) {
+    if (e.source == LBM_SRC_CONST) return (T)e.value;
+    if (e.source == LBM_SRC_PARABOLA) {
+        T cx = T(b.nx - 1) / T(2.0), cz = T(b.nz - 1) / T(2.0), r = T(b.nx - 1) / T(2.0);
+        T dx = T(gx) - cx, dz = T(gz) - cz;
+        return (T)e.value * (T(1.0) - (dx * dx + dz * dz) / (r * r));
+    }
+    if (e.source == LBM_SRC_PLANE_INLET) return plane_in[gx + (long long)gz * b.nx];
+    return plane_out[gx + (long long)gz * b.nx];
+}
+
 // initial velocity of the cell with label g at GLOBAL coordinates (x,y,z); zero for cells the
 // reference does not store (label 0) and outside the box
 template <typename T>

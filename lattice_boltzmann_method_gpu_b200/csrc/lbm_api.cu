@@ -170,6 +170,9 @@ struct Solver final : SolverBase {
     // in-place sparse storage: its own numbering (fluid nodes + single-cell x gaps), see lbm_geo.cu k_span_flags
     int32_t *d_sid = nullptr;
     uint2 *d_cmeta = nullptr;
+    uint32_t *d_rec_links = nullptr;
+    int32_t *d_bcslot = nullptr;     // in-place sparse storage: precomputed inlet / outlet link lists (k_bc_links)
+    BcLink<T> *d_bclinks = nullptr;
     std::vector<long long> sid_plane_first;      // [planes of the state box + 1] first own-numbering id of each plane
     long long own_id0 = 0, own_id1 = 0;          // ids (storage numbering, local) of the owned planes
     long long halo_id0[2] = {0, 0}, halo_n[2] = {0, 0};   // compact range of the halo plane per side
@@ -184,7 +187,7 @@ struct Solver final : SolverBase {
         fr(d_flag), fr(d_label_ext), fr(d_label), fr(d_index), fr(d_scratch), fr(d_node), fr(d_seg), fr(d_label8);
         fr(d_fa), fr(d_fb == d_fa ? nullptr : d_fb), fr(d_rho), fr(d_ux), fr(d_uy), fr(d_uz), fr(d_plane_in), fr(d_plane_out);
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
-        fr(d_sid), fr(d_cmeta);
+        fr(d_sid), fr(d_cmeta), fr(d_rec_links), fr(d_bcslot), fr(d_bclinks);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
         fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count), fr(d_pulse), fr(d_barrier);
         if (ev0) cudaEventDestroy(ev0);
@@ -231,7 +234,7 @@ struct Solver final : SolverBase {
         dfree(&d_fa), dfree(&d_fb), dfree(&d_rho), dfree(&d_ux), dfree(&d_uy), dfree(&d_uz);
         for (int sd = 0; sd < 2; sd++) dfree(&d_send[sd]), dfree(&d_recv[sd]);
         dfree(&d_cart), dfree(&d_nodec), dfree(&d_wallc), dfree(&d_labelc), dfree(&d_rec), dfree(&d_chunk_cnt);
-        dfree(&d_cmeta);
+        dfree(&d_cmeta), dfree(&d_rec_links), dfree(&d_bcslot), dfree(&d_bclinks);
         dfree(&d_chunk_off), dfree(&d_plane_seg);
         if (d_stage) cudaFree(d_stage), d_stage = nullptr, stage_elems = 0;
         d_cur = d_nxt = nullptr;
@@ -651,7 +654,23 @@ struct Solver final : SolverBase {
         if (aa) {
             if (!d_cmeta && dalloc(&d_cmeta, (size_t)(ns / 32 + 2))) return LBM_ERR_NOMEM;
             CK(launch_chunk_meta(d_nodec, ns, d_cmeta, st));
-            launches++;
+            dfree(&d_rec_links);
+            if (dalloc(&d_rec_links, (size_t)std::max<long long>(nseg, 1) * 32)) return LBM_ERR_NOMEM;
+            CK(launch_rec_links(d_rec, d_nodec, nseg, d_rec_links, st));
+            launches += 2;
+            // inlet / outlet link lists (two passes: size, fill)
+            int *d_tot = (int *)(d_cnt + 7), total = 0;
+            CK(cudaMemsetAsync(d_tot, 0, sizeof(int), st));
+            CK(launch_bc_links<T>(d_nodec, d_wallc, d_cart, d_label8, box, bc, d_plane_in, d_plane_out, own_id0, own_id1, d_tot, nullptr,
+                                  nullptr, st));
+            CK(cudaMemcpyAsync(&total, d_tot, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            dfree(&d_bcslot), dfree(&d_bclinks);
+            if (dalloc(&d_bcslot, (size_t)std::max<long long>(ns, 1)) || dalloc(&d_bclinks, (size_t)std::max(total, 1))) return LBM_ERR_NOMEM;
+            CK(cudaMemsetAsync(d_tot, 0, sizeof(int), st));
+            CK(launch_bc_links<T>(d_nodec, d_wallc, d_cart, d_label8, box, bc, d_plane_in, d_plane_out, own_id0, own_id1, d_tot, d_bcslot,
+                                  d_bclinks, st));
+            launches += 2;
         }
         qstride = (ns + 64 + 31) & ~31LL;  // every direction's array starts 256-byte aligned
         if (aa && qstride >= (1LL << 31) / 3) FAIL(LBM_ERR_ARG, "slab of %lld nodes is too large for 32-bit element offsets: use more z-slabs", ns);
@@ -737,7 +756,7 @@ struct Solver final : SolverBase {
             const long long zA = c0 / box.plane - (own_z0 - box.z0), zB = c1 / box.plane - (own_z0 - box.z0);
             sp.seg_begin = seg_plane_start[(size_t)zA], sp.seg_end = seg_plane_start[(size_t)zB];
             if (d.storage == LBM_STORE_SPARSE_AA) {
-                sp.cartc = d_cart, sp.cmeta = d_cmeta;
+                sp.cartc = d_cart, sp.cmeta = d_cmeta, sp.rec_links = d_rec_links, sp.bcslot = d_bcslot, sp.bclinks = d_bclinks;
                 sp.id_begin = sid_plane_first[(size_t)(c0 / box.plane)], sp.id_end = sid_plane_first[(size_t)(c1 / box.plane)];
                 sp.halo_lo_n = (int)halo_n[0], sp.halo_hi0 = (int)halo_id0[1];
                 if (sp.base.parity == 0 ? sp.id_end <= sp.id_begin : sp.seg_end <= sp.seg_begin) return 0;
@@ -764,7 +783,7 @@ struct Solver final : SolverBase {
     size_t pulse_cap = 0;
     unsigned *d_barrier = nullptr;
     int sm_count = 0;
-    static constexpr int PERSIST_MAX_STEPS = 2048;
+    static constexpr int PERSIST_MAX_STEPS = 2048, PERSIST_BAR_WORDS = 64 + 32 * 64;  // = BAR_WORDS of step_sparse_aa.cuh
     int opt_persist = -1;  // lbm_set_option("persistent", 0 / 1); -1: by size
     bool use_persist() {
         if (d.storage != LBM_STORE_SPARSE_AA || lo_halo || hi_halo) return false;
@@ -782,7 +801,7 @@ struct Solver final : SolverBase {
             cudaDeviceProp prop;
             CK(cudaGetDeviceProperties(&prop, d.device));
             sm_count = prop.multiProcessorCount;
-            CK(cudaMalloc((void **)&d_barrier, sizeof(unsigned)));
+            CK(cudaMalloc((void **)&d_barrier, PERSIST_BAR_WORDS * sizeof(unsigned)));
         }
         const T *pulse_dev = nullptr;
         if (d.pulse_amp != 0.0) {  // the same scale the single launches get, step by step (make_params)
@@ -797,10 +816,11 @@ struct Solver final : SolverBase {
             CK(cudaStreamSynchronize(st));  // `tab` is pageable and goes out of scope
             pulse_dev = d_pulse;
         }
-        CK(cudaMemsetAsync(d_barrier, 0, sizeof(unsigned), st));
+        CK(cudaMemsetAsync(d_barrier, 0, PERSIST_BAR_WORDS * sizeof(unsigned), st));
         SparseParams<T> sp{};
         sp.base = make_params(plane_c(own_z0), plane_c(own_z1), nullptr);
-        sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc, sp.spw = 1, sp.cartc = d_cart, sp.cmeta = d_cmeta;
+        sp.rec = d_rec, sp.nodec = d_nodec, sp.wallc = d_wallc, sp.spw = 1, sp.cartc = d_cart, sp.cmeta = d_cmeta, sp.rec_links = d_rec_links;
+        sp.bcslot = d_bcslot, sp.bclinks = d_bclinks;
         sp.seg_begin = seg_plane_start[0], sp.seg_end = seg_plane_start[(size_t)(own_z1 - own_z0)];
         sp.id_begin = own_id0, sp.id_end = own_id1;
         sp.halo_lo_n = 0, sp.halo_hi0 = INT32_MAX;

@@ -642,6 +642,62 @@ __global__ void k_seg_fill_rows(const uint32_t *nodec, const long long *cart, Ro
     o[22] = (links & piece) ? 1 : 0;
     if (r.my_slot == 0) atomicMin(plane_seg + (r.cartc / b.plane - own_zl0), seg);
 }
+// Inlet / outlet links of the in-place sparse storage, precomputed once per initialize(): the same decisions
+// boundary_node (step_dense.cuh) takes every step -- source label, is the direction in that label's set, which
+// speed does the source node prescribe -- stored as a short list per node.
+template <typename T>
+__global__ void k_bc_links(const uint32_t *nodec, const uint32_t *wallc, const long long *cart, const int8_t *label8, Box b,
+                           BcTable bc, const T *plane_in, const T *plane_out, long long i0, long long i1, int *total,
+                           int32_t *bcslot, BcLink<T> *links) {
+    const long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const uint32_t node = nodec[i];
+    if ((node & NODE_SKIP) || !(node & NODE_HAS_BC)) return;
+    const uint32_t rest = node & NODE_LINKS & ~wallc[i];
+    const long long c = cart[i];
+    const Coord co = coord_of(b, c);
+    uint32_t bcm = 0u;
+    int lab[Q];
+    for (int q = 1; q < Q; q++) {
+        lab[q] = 0;
+        if (!(rest & (1u << q))) continue;
+        const int l = label8[c - ((long long)cxq(q) + (long long)b.px * cyq(q) + b.plane * czq(q))];
+        lab[q] = l;
+        if (l >= 2 && l < LBM_MAX_BC && bc.e[l].kind != LBM_BC_NONE && caxis(q, bc.e[l].naxis) == bc.e[l].nsign) bcm |= 1u << q;
+    }
+    const int n = 1 + __popc(bcm);
+    if (!links) {
+        atomicAdd(total, n);
+        return;
+    }
+    const int slot = atomicAdd(total, n);
+    bcslot[i] = slot;
+    BcLink<T> *o = links + slot;
+    o[0].meta = bcm, o[0].pad = 0u, o[0].ubc = T(0);
+    int k = 1;
+    for (int q = 1; q < Q; q++) {
+        if (!(bcm & (1u << q))) continue;
+        const BcEntry &e = bc.e[lab[q]];
+        o[k].meta = (uint32_t)e.kind | ((uint32_t)(caxis(q, e.vaxis) + 1) << 2) | (e.pulsatile ? 16u : 0u);
+        o[k].pad = 0u;
+        // the speed is sampled at the boundary node s = x - c_q itself (pos.cu:597)
+        o[k].ubc = e.kind == LBM_BC_P ? T(0) : bc_speed_unscaled<T>(e, b, plane_in, plane_out, co.x - cxq(q), co.z - czq(q));
+        k++;
+    }
+}
+// One link word per lane of every record (NODE_SKIP for lanes outside the record's pieces): the neighbour
+// (odd) step of the in-place storage loads it NEXT TO the record instead of fetching the node word by the
+// compact id the record holds, which took a dependent round trip to memory out of every warp's life.
+__global__ void k_rec_links(const int32_t *rec, const uint32_t *nodec, long long nseg, uint32_t *links) {
+    const long long seg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (seg >= nseg) return;
+    const int32_t *r = rec + seg * SEG_REC;
+    const int mA = r[19], mB = r[SEG_HALF + 19];
+    const bool inA = lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8);
+    const bool inB = (mB >> 8) != 0 && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
+    links[seg * 32 + lane] = (inA || inB) ? nodec[r[0] + lane] : NODE_SKIP;
+}
 // exclusive scan of int32 counts into int64 offsets (single block, carry across chunks)
 __global__ void k_scan_i32(const int32_t *counts, long long *offsets, long long n, long long *total_out) {
     __shared__ long long carry;
@@ -1012,6 +1068,22 @@ cudaError_t launch_build_segments_rows(const uint32_t *nodec, const long long *c
     }
     return cudaGetLastError();
 }
+template <typename T>
+cudaError_t launch_bc_links(const uint32_t *nodec, const uint32_t *wallc, const long long *cart, const int8_t *label8, Box box,
+                            const BcEntry *bc, const T *plane_in, const T *plane_out, long long i0, long long i1,
+                            int *total_dev, int32_t *bcslot, BcLink<T> *links, cudaStream_t s) {
+    if (i1 <= i0) return cudaSuccess;
+    BcTable t;
+    for (int i = 0; i < LBM_MAX_BC; i++) t.e[i] = bc[i];
+    k_bc_links<T><<<nblocks(i1 - i0, 128), 128, 0, s>>>(nodec, wallc, cart, label8, box, t, plane_in, plane_out, i0, i1, total_dev,
+                                                        bcslot, links);
+    return cudaGetLastError();
+}
+cudaError_t launch_rec_links(const int32_t *rec, const uint32_t *nodec, long long nseg, uint32_t *links, cudaStream_t s) {
+    if (nseg <= 0) return cudaSuccess;
+    k_rec_links<<<nblocks(nseg * 32, 256), 256, 0, s>>>(rec, nodec, nseg, links);
+    return cudaGetLastError();
+}
 cudaError_t launch_span_flags(const int32_t *label, Box box, int fluid_label, int32_t *keep, cudaStream_t s) {
     k_span_flags<<<nblocks(box.cells(), 256), 256, 0, s>>>(label, box, fluid_label, keep);
     return cudaGetLastError();
@@ -1079,6 +1151,9 @@ cudaError_t launch_halo_unpack_sparse(T *f, long long qstride, const int8_t *lab
                                                  int, int, double *, cudaStream_t);                                     \
     template cudaError_t launch_halo_pack<T>(const T *, long long, Box, int, int, T *, cudaStream_t);                   \
     template cudaError_t launch_init_sparse<T>(const InitParams<T> &, const long long *, long long, cudaStream_t);      \
+    template cudaError_t launch_bc_links<T>(const uint32_t *, const uint32_t *, const long long *, const int8_t *, Box, \
+                                            const BcEntry *, const T *, const T *, long long, long long, int *,         \
+                                            int32_t *, BcLink<T> *, cudaStream_t);                                      \
     template cudaError_t launch_gather_pops_sparse_aa<T>(const T *, long long, const int32_t *, const int32_t *,        \
                                                          const int32_t *, Box, int, int, int, long long, long long,     \
                                                          int, T *, cudaStream_t);                                       \

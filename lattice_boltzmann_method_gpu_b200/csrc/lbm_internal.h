@@ -94,6 +94,16 @@ struct StepParams {
     unsigned int chk_launch;
 };
 
+// Precomputed inlet / outlet links of the in-place sparse storage: per node with NODE_HAS_BC a header
+// (mask of the links that take the non-equilibrium extrapolation) followed by one entry per set bit, in
+// direction order.  The step kernel then needs no label look-ups, coordinates or profile evaluation.
+template <typename T>
+struct BcLink {
+    uint32_t meta;  // header: link mask.  entry: bits 0-1 lbm_bc_kind, bits 2-3 c_q[vel_axis] + 1, bit 4 pulsatile
+    uint32_t pad;
+    T ubc;          // prescribed speed at the source node (before the pulsatile scale)
+};
+
 template <typename T>
 struct InitParams {
     T *fa, *fb;  // both buffers (fb == fa for in-place storage)
@@ -176,6 +186,12 @@ cudaError_t launch_gather_pops_sparse_aa(const T *a, long long qstride, const in
 // the in-place sparse storage's own numbering (fluid nodes + single-cell x gaps), its records and chunk masks
 cudaError_t launch_span_flags(const int32_t *label, Box box, int fluid_label, int32_t *keep, cudaStream_t s);
 cudaError_t launch_chunk_meta(const uint32_t *nodec, long long ns, uint2 *meta, cudaStream_t s);
+// pass 1 (links == nullptr): *total_dev += entries needed; pass 2: lists filled, slots handed out by atomics
+template <typename T>
+cudaError_t launch_bc_links(const uint32_t *nodec, const uint32_t *wallc, const long long *cart, const int8_t *label8, Box box,
+                            const BcEntry *bc, const T *plane_in, const T *plane_out, long long i0, long long i1,
+                            int *total_dev, int32_t *bcslot, BcLink<T> *links, cudaStream_t s);
+cudaError_t launch_rec_links(const int32_t *rec, const uint32_t *nodec, long long nseg, uint32_t *links, cudaStream_t s);
 cudaError_t launch_build_segments_rows(const uint32_t *nodec, const long long *cart, const int32_t *sid, const int32_t *label,
                                        int fluid_label, Box box, int own_zl0, long long id0, long long id1, int32_t *counts,
                                        long long *offsets, long long *nseg_dev, int32_t *rec, long long *plane_seg,
@@ -203,6 +219,9 @@ struct SparseParams {
     // in-place sparse storage (step_sparse_aa.cuh)
     const long long *cartc;  // Cartesian cell of a compact id (boundary slow path)
     const uint2 *cmeta;      // per aligned chunk of 32 ids: fluid-lane mask, "some lane has a non-wall link"
+    const uint32_t *rec_links;  // [nseg][32] node word of every lane of a record (NODE_SKIP outside its pieces)
+    const int32_t *bcslot;      // per id: first BcLink of the node's list (nodes with NODE_HAS_BC only)
+    const BcLink<T> *bclinks;
     long long id_begin, id_end;  // compact ids of the even (local) step's launch
     int halo_lo_n, halo_hi0;     // local ids < halo_lo_n lie in the low halo plane, ids >= halo_hi0 in the high one
     int dk[Q];                   // (k - opp k) * qstride: from the array of opp(k) to the same node's slot in the array of k

@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include "lattice.cuh"
 #include "lbm_internal.h"
+#include "init_rule.cuh"
 
 namespace lbm {
 
@@ -70,20 +71,7 @@ __device__ __noinline__ void chk_touch(const StepParams<T> &p, const T *a, bool 
 // prescribed boundary speed of BC entry `e` at boundary node (gx, gy, gz) (global coords)
 template <typename T>
 __device__ __forceinline__ T bc_speed(const StepParams<T> &p, const BcEntry &e, int gx, int gz, T pulse) {
-    T u;
-    if (e.source == LBM_SRC_CONST) {
-        u = (T)e.value;
-    } else if (e.source == LBM_SRC_PARABOLA) {
-        // pos.cu:597 -- evaluated at the boundary node's own (i,k); squares of
-        // half-integers are exact, so a*a equals the reference's powf(a,2)
-        T cx = T(p.box.nx - 1) / T(2.0), cz = T(p.box.nz - 1) / T(2.0), r = T(p.box.nx - 1) / T(2.0);
-        T dx = T(gx) - cx, dz = T(gz) - cz;
-        u = (T)e.value * (T(1.0) - (dx * dx + dz * dz) / (r * r));
-    } else if (e.source == LBM_SRC_PLANE_INLET) {
-        u = p.plane_in[gx + (long long)gz * p.box.nx];
-    } else {
-        u = p.plane_out[gx + (long long)gz * p.box.nx];
-    }
+    T u = bc_speed_unscaled<T>(e, p.box, p.plane_in, p.plane_out, gx, gz);
     if (e.pulsatile) u = u * pulse;
     return u;
 }

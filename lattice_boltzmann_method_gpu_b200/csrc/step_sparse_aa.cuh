@@ -59,21 +59,39 @@ __device__ __forceinline__ T ld_pop(const T *a) {
     return CG ? __ldcg(a) : *a;
 }
 
-// inlet / outlet links of a node, after its collision: the extrapolated value goes into the own slot
+// inlet / outlet links of a node, after its collision: the non-equilibrium extrapolation value
+//     feq_q(rho_bc, u_bc(s)) + (g_q(x) - feq_q(rho_x, u_x)) (1 - 1/tau)          (bif:877-1021, step_dense.cuh)
+// goes into the node's own slot.  Which links, of which kind, with which prescribed speed was worked out once
+// by k_bc_links (lbm_geo.cu); here the 18 directions are unrolled with compile-time q, so a boundary node costs
+// a few dozen instructions per link instead of the ~3600-instruction generic path -- on a 64^3 grid the nodes
+// under the lid / at the inlet otherwise set the duration of every step.
 template <typename T>
-__device__ __forceinline__ void own_slot_bc(const StepParams<T> &p, long long cart, long long i, uint32_t rest, T rho, T ux,
-                                            T uy, T uz, const T (&f)[Q], T pulse) {
-    T gl[Q], hv[Q];
+__device__ __forceinline__ void own_slot_bc(const SparseParams<T> &sp, long long i, T rho, T ux, T uy, T uz,
+                                            const T (&f)[Q], T pulse) {
+    const StepParams<T> &p = sp.base;
+    const BcLink<T> *L = sp.bclinks + sp.bcslot[i];
+    const uint32_t bcm = L[0].meta;
+    const T r3 = rho / T(3.0), r18 = rho / T(18.0), r36 = rho / T(36.0);
+    const T one = T(1.0);
+    int e = 1;
 #pragma unroll
-    for (int q = 0; q < Q; q++) gl[q] = f[q];
-    // static links report no value (mode MODE_AB): their slot is left alone
-    const uint32_t wm = boundary_node<T>(p, cart, rest, MODE_AB, rho, ux, uy, uz, gl, gl, hv, pulse);
-#pragma unroll
-    for (int q = 1; q < Q; q++)
-        if (wm & (1u << q)) {
-            LBM_CHK(p, p.store_base[q] + i);
-            p.store_base[q][i] = hv[q];
+    for (int q = 1; q < Q; q++) {
+        if (!(bcm & (1u << q))) continue;
+        const BcLink<T> l = L[e++];
+        const int kind = (int)(l.meta & 3u), cs = (int)((l.meta >> 2) & 3u) - 1;
+        T u = l.ubc;
+        if (l.meta & 16u) u = u * pulse;
+        const T feq = feq_lit<T>(q, r3, r18, r36, ux, uy, uz);
+        T tmp;
+        if (kind == LBM_BC_P) {
+            tmp = feq_lit<T>(q, one / T(3.0), one / T(18.0), one / T(36.0), ux, uy, uz);
+        } else {
+            const T rw = kind == LBM_BC_V ? (q < 7 ? r18 : r36) : (q < 7 ? one / T(18.0) : one / T(36.0));
+            tmp = feq_bc_axis<T>(rw, cs, u);
         }
+        LBM_CHK(p, p.store_base[q] + i);
+        p.store_base[q][i] = tmp + (f[q] - feq) * p.om1;
+    }
 }
 
 // per-step switches that are template parameters of the one-step kernels and run-time values of the
@@ -115,7 +133,7 @@ __device__ __forceinline__ void aa_even_node(const SparseParams<T> &sp, long lon
                 LBM_CHK(p, p.store_base[q] + i);
                 p.store_base[q][i] = f[oppq(q)];
             }
-        if (node & NODE_HAS_BC) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f, pulse);
+        if (node & NODE_HAS_BC) own_slot_bc<T>(sp, i, rho, ux, uy, uz, f, pulse);
     }
     if (st.moments) {
         p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
@@ -131,10 +149,12 @@ __device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long lo
     const int lane = threadIdx.x & 31;
     const int32_t r0 = sp.rec[seg * SEG_REC + lane];
     const int32_t r1 = lane < SEG_REC - 32 ? sp.rec[seg * SEG_REC + 32 + lane] : 0;
-    const int mA = __shfl_sync(0xffffffffu, r0, 19), mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
+    // the lane's node word travels with the record (no dependent load): link bits, NODE_SKIP when idle
+    const uint32_t node = sp.rec_links[seg * 32 + lane];
+    const int mB = __shfl_sync(0xffffffffu, r1, SEG_HALF + 19 - 32);
     const bool two = (mB >> 8) != 0;  // warp-uniform
     const bool inB = two && lane >= (mB & 255) && lane < (mB & 255) + (mB >> 8);
-    const bool active = inB || (lane >= (mA & 255) && lane < (mA & 255) + (mA >> 8));
+    const bool active = !(node & NODE_SKIP);
     const int i = __shfl_sync(0xffffffffu, r0, 0) + lane;  // compact id: the chunk's first id + lane in both pieces
     // compact id of the node at this lane's x in each of the 8 neighbouring rows
     int j[8];
@@ -148,13 +168,7 @@ __device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long lo
         }
         j[r] = b + lane;
     }
-    int has_links = __shfl_sync(0xffffffffu, r0, 22);
-    if (two) {
-        const int bl = __shfl_sync(0xffffffffu, r1, SEG_HALF + 22 - 32);
-        has_links = inB ? bl : has_links;
-    }
     if (!active) return;
-    const uint32_t node = has_links ? sp.nodec[i] : 0u;
     // ONE element index per direction, used for the load and for the store: inside the array of opp(k),
     // either the source's id or -- for a link -- this node's own slot in the array of k, which lies
     // dk[k] = (k - opp k) * qstride elements away
@@ -192,7 +206,7 @@ __device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long lo
         LBM_CHK(p, p.store_base[oppq(k)] + idx[k]);
         p.store_base[oppq(k)][idx[k]] = f[oppq(k)];
     }
-    if (rest && (node & NODE_HAS_BC)) own_slot_bc<T>(p, sp.cartc[i], i, rest, rho, ux, uy, uz, f, pulse);
+    if (rest && (node & NODE_HAS_BC)) own_slot_bc<T>(sp, i, rho, ux, uy, uz, f, pulse);
     if (st.moments) {
         p.rho[i] = rho, p.ux[i] = ux, p.uy[i] = uy, p.uz[i] = uz;
     }
@@ -240,17 +254,30 @@ struct PersistArgs {
     int moments_last, resid;
     double *S;          // [nsteps] when resid
     const T *pulse;     // [nsteps] or null (scale 1)
-    unsigned *barrier;  // zero at launch
+    unsigned *barrier;  // BAR_WORDS words, zero at launch
 };
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target) {
+// Grid barrier, generation `gen` = 1, 2, ... (counters are monotonic, never reset inside a launch).
+// Same-address atomics serialise in L2 at ~27 cycles each and polling loads queue behind them, so a single
+// counter for ~300 CTAs made the barrier cost more than the step (19 us per 64^3 step).  Two levels: CTAs
+// arrive on the counter of their group of 16, the last arriver of a group arrives on the top counter, the
+// last of those publishes `gen` in a release word that everybody polls with plain L1-bypassing loads.
+// Every counter sits in its own 128-byte line: bar[0] release, bar[32] top, bar[64 + 32 g] group g.
+constexpr int BAR_GROUP = 16, BAR_WORDS = 64 + 32 * 64;
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(counter, 1u);
+        const unsigned g = blockIdx.x / BAR_GROUP, ngroups = (gridDim.x + BAR_GROUP - 1) / BAR_GROUP;
+        const unsigned gsize = min((unsigned)BAR_GROUP, gridDim.x - g * BAR_GROUP);
+        if (atomicAdd(bar + 64 + 32 * g, 1u) == gen * gsize - 1u) {
+            if (atomicAdd(bar + 32, 1u) == gen * ngroups - 1u) {
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(gen) : "memory");
+            }
+        }
         unsigned v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < target);
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < gen);
         __threadfence();
     }
     __syncthreads();
@@ -280,7 +307,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
                 aa_odd_record<T, STRICT, false, true>(sp, seg, st, pulse, velsum);
         }
         if (st.resid) warp_add(pa.S + s, velsum);
-        if (s + 1 < pa.nsteps) grid_barrier(pa.barrier, (unsigned)(s + 1) * gridDim.x);
+        if (s + 1 < pa.nsteps) grid_barrier(pa.barrier, (unsigned)(s + 1));
     }
 }
 template <typename T, bool STRICT>
@@ -298,7 +325,7 @@ cudaError_t launch_sparse_aa_persist_impl(const SparseParams<T> &p_in, const Per
     per_sm = std::min(per_sm, sizeof(T) == 8 ? 1 : 2);
     const long long work = std::max((p.id_end - p.id_begin + 31) / 32 + 1, p.seg_end - p.seg_begin);
     long long blocks = std::min<long long>((long long)sm_count * per_sm, (work + PERSIST_BLOCK / 32 - 1) / (PERSIST_BLOCK / 32));
-    if (blocks < 1) blocks = 1;
+    blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)BAR_GROUP * 64));
     PersistArgs<T> a = pa;
     void *args[2] = {(void *)&p, (void *)&a};
     return cudaLaunchCooperativeKernel((const void *)k_sparse_aa_persist<T, STRICT>, dim3((unsigned)blocks), dim3(PERSIST_BLOCK), args, 0, s);

@@ -98,14 +98,24 @@ def test_gpu_reproduces_the_coronary_program(storage_name, from_file, tmp_path):
     V, D = cor_blocks(geo, idx, *c.get_fields())
     compare_cor(V, D, 2e-5)
     if from_file:  # the writer: same header lines, three sections, values parse back to the same blocks
-        lines = (tmp_path / "coronary_1000.vtk").open().read(600).split("\\n")[:8]
+        lines = (tmp_path / "coronary_1000.vtk").open().read(600).split("\n")[:8]
         assert lines == [str(s) for s in G["cor_header"]]
-        with open(tmp_path / "coronary_1000.vtk") as f:
-            txt = f.read()
-        assert txt.count("SCALARS DENSITY float") == 1 and txt.count("SCALARS PRESSURE float") == 1 and txt.count("VECTORS VELOCITY float") == 1
-        body = txt.split("VECTORS VELOCITY float\\n")[1]
-        Vf = np.array(body.split(), dtype=np.float32).reshape(V.shape)
-        assert float(np.abs(Vf - V).max()) <= 1e-5 * float(G["cor_max_abs"])
+        sections = {}
+        with open(tmp_path / "coronary_1000.vtk") as f:  # three sections of one (long) line each, cor:960-1008
+            while True:
+                line = f.readline()
+                if not line:
+                    break
+                if line.startswith("SCALARS"):
+                    f.readline()
+                    sections[line.split()[1]] = np.fromstring(f.readline(), dtype=np.float32, sep=" ")
+                elif line.startswith("VECTORS"):
+                    sections[line.split()[1]] = np.fromstring(f.readline(), dtype=np.float32, sep=" ")
+        assert sorted(sections) == ["DENSITY", "PRESSURE", "VELOCITY"]
+        assert float(np.abs(sections["VELOCITY"].reshape(V.shape) - V).max()) <= 1e-5 * float(G["cor_max_abs"])
+        assert float(np.abs(sections["DENSITY"].reshape(D.shape) - D).max()) <= 1e-5 * float(C_RHO)
+        C_pre = C_RHO * C_U * C_U
+        assert np.allclose(sections["PRESSURE"].reshape(D.shape), D / C_RHO * C_pre / 3.0, rtol=2e-5)
 
 
 @pytest.mark.gpu
