@@ -7,8 +7,9 @@
 //   STRICT : the reference's expression order (bif.cu:574-634), compiled in a
 //            translation unit built with -fmad=false, so results are
 //            bit-identical to the CPU oracle (gcc -ffp-contract=off).
-//   FAST   : algebraically equal, reciprocal-multiply, FMA-contracted form --
-//            the measured path.  Agreement with STRICT is tolerance-tested.
+//   FAST   : algebraically equal, reciprocal-multiply form with EXPLICIT fma()s (its translation
+//            unit is built with -fmad=false as well) -- the measured path.  Agreement with
+//            STRICT is tolerance-tested; every kernel variant agrees with every other bit for bit.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -172,7 +173,12 @@ __device__ __forceinline__ void collide_bgk(T (&f)[Q], T tau, T inv_tau, T &rho,
             f[q] = f[q] - (f[q] - feq) / tau;
         }
     } else {
-        // pairwise sums shorten the dependency chains; order is free in FAST mode
+        // pairwise sums shorten the dependency chains; order is free in FAST mode.
+        // Every multiply-add below is an EXPLICIT fma and the translation unit is compiled with -fmad=false
+        // like the STRICT one: which operations fuse is then decided here, not by ptxas per kernel
+        // instantiation, so all storages, the persistent kernel, the two-segment kernel and the slab (peer
+        // store) variants produce the same bits from the same inputs -- "N slabs == 1 domain" and
+        // "in-place == two buffers" hold bit for bit in FAST arithmetic too.
         T a0 = f[1] + f[2], a1 = f[3] + f[4], a2 = f[5] + f[6];
         T d0 = f[7] + f[10], d1 = f[8] + f[9], d2 = f[11] + f[14], d3 = f[12] + f[13], d4 = f[15] + f[18],
           d5 = f[16] + f[17];
@@ -189,21 +195,21 @@ __device__ __forceinline__ void collide_bgk(T (&f)[Q], T tau, T inv_tau, T &rho,
         // tau < 1 and is 3-10x less accurate in fp32 (measured, profiles/r01_notes.md).
         const T om = inv_tau;
         // feq_q = rho w_q (1 + 3cu + 4.5cu^2 - 1.5u^2)
-        const T base = T(1.0) - T(1.5) * (ux * ux + uy * uy + uz * uz);
+        const T base = fma(T(-1.5), fma(ux, ux, fma(uy, uy, uz * uz)), T(1.0));
         // rho w_q must not carry a systematic error: multiplying by a rounded 1/18 gives every cell
         // the same signed error in sum_q feq_q, i.e. a coherent mass drift of ~2 ulp per step
         // (visible in fp32 after 1000 steps; the reference divides, rho/18).  A division costs
         // ~10 (fp32) / ~25 (fp64) dependent instructions on a latency-bound kernel, so the weight is
         // applied as an error-free two-term product instead (rho_over).
         const T k0 = rho_over<T>(r, 3), k1 = rho_over<T>(r, 18), k2 = T(0.5) * k1;
-        f[0] = f[0] + om * (k0 * base - f[0]);
+        f[0] = fma(om, fma(k0, base, -f[0]), f[0]);
 #define LBM_PAIR(qp, qm, cu, kw)                                    \
     {                                                               \
         T cu_ = (cu);                                               \
-        T even = base + T(4.5) * cu_ * cu_;                         \
+        T even = fma(T(4.5) * cu_, cu_, base);                      \
         T odd = T(3.0) * cu_;                                       \
-        f[qp] = f[qp] + om * ((kw) * (even + odd) - f[qp]);         \
-        f[qm] = f[qm] + om * ((kw) * (even - odd) - f[qm]);         \
+        f[qp] = fma(om, fma((kw), even + odd, -f[qp]), f[qp]);      \
+        f[qm] = fma(om, fma((kw), even - odd, -f[qm]), f[qm]);      \
     }
         LBM_PAIR(1, 2, ux, k1)
         LBM_PAIR(3, 4, uy, k1)

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <fstream>
 #include <iostream>
 #include <new>
@@ -179,7 +181,7 @@ struct Solver final : SolverBase {
     long long face_id0[2] = {0, 0}, face_n[2] = {0, 0};   // compact range of the outermost owned plane per side
 
     ~Solver() override {
-        if (writer.joinable()) writer.join();
+        join_writer();
         cudaSetDevice(d.device);
         auto fr = [](void *p) {
             if (p) cudaFree(p);
@@ -1509,7 +1511,7 @@ struct Solver final : SolverBase {
     }
     int write_ascii(int t) { return write_ascii_from(t, w_rho.data(), w_ux.data(), w_uy.data(), w_uz.data(), err); }
     // formats and writes one file from host arrays; touches no other member that a running time loop changes
-    int write_ascii_from(int t, const T *prho, const T *pux, const T *puy, const T *puz, std::string &errout) {
+    int write_ascii_from(int t, const T *prho, const T *pux, const T *puy, const T *puz, std::string &errout, int max_threads = 16) {
         const int NX = d.nx, NY = d.ny, NZ = d.nz;
         const float CH = (float)d.CH, C_U = (float)d.C_U, C_rho = (float)d.C_rho;
         const float C_pre = C_rho * C_U * C_U;
@@ -1538,7 +1540,7 @@ struct Solver final : SolverBase {
         // the reference's ASCII writer would otherwise dominate the run.
         // z-planes are formatted by several host threads into their own buffers and written in order.
         const int nzp = z1 - z0;
-        const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, nzp}));
+        const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), max_threads, nzp}));
         auto put = [](std::string &buf, auto v) { vtk_put(buf, v); };
         // kind 0: density, 1: pressure, 2: velocity
         auto format_planes = [&](int kind, std::vector<std::string> &parts) {
@@ -1584,26 +1586,45 @@ struct Solver final : SolverBase {
         return 0;
     }
 
-    // ---- periodic dumps of the run loops are formatted and written by a helper thread while the GPU
-    // keeps stepping (at 64^3 one ASCII dump costs as much host time as ~2000 steps of device time)
-    std::thread writer;
-    std::vector<T> a_rho, a_ux, a_uy, a_uz;  // the snapshot the helper thread reads
-    int writer_rc = 0;
-    std::string writer_err;
+    // ---- periodic dumps of the run loops are formatted and written by helper threads while the GPU keeps
+    // stepping: at 64^3 one ASCII dump takes as long as ~1000 steps, and the reference dumps every 500, so up
+    // to MAX_DUMPS_IN_FLIGHT snapshots are being written at any time
+    struct DumpJob {
+        std::thread th;
+        std::vector<T> rho, ux, uy, uz;  // the snapshot the helper thread reads
+        int rc = 0;
+        std::string err;
+    };
+    std::deque<std::unique_ptr<DumpJob>> dump_jobs;
+    static constexpr size_t MAX_DUMPS_IN_FLIGHT = 4;
+    static constexpr int ASYNC_DUMP_THREADS = 3;  // per dump: 12 formatting threads at most, the launching thread keeps a core
+    int join_oldest_dump() {
+        auto &j = dump_jobs.front();
+        if (j->th.joinable()) j->th.join();
+        const int rc = j->rc;
+        if (rc) err = j->err;
+        dump_jobs.pop_front();
+        return rc;
+    }
     int join_writer() {
-        if (writer.joinable()) writer.join();
-        const int rc = writer_rc;
-        writer_rc = 0;
-        if (rc) err = writer_err;
+        int rc = 0;
+        while (!dump_jobs.empty()) {
+            const int r = join_oldest_dump();
+            if (r && !rc) rc = r;
+        }
         return rc;
     }
     // w_rho .. w_uz were just fetched (fetch_for_output)
     int save_fetched_async(int t) {
         if (out_format != LBM_OUT_ASCII_VTK) return output_save_binary(t);
-        int r = join_writer();  // at most one dump in flight
-        if (r) return r;
-        a_rho = w_rho, a_ux = w_ux, a_uy = w_uy, a_uz = w_uz;
-        writer = std::thread([this, t]() { writer_rc = write_ascii_from(t, a_rho.data(), a_ux.data(), a_uy.data(), a_uz.data(), writer_err); });
+        while (dump_jobs.size() >= MAX_DUMPS_IN_FLIGHT) {
+            int r = join_oldest_dump();
+            if (r) return r;
+        }
+        dump_jobs.emplace_back(new DumpJob());
+        DumpJob *j = dump_jobs.back().get();
+        j->rho = w_rho, j->ux = w_ux, j->uy = w_uy, j->uz = w_uz;
+        j->th = std::thread([this, j, t]() { j->rc = write_ascii_from(t, j->rho.data(), j->ux.data(), j->uy.data(), j->uz.data(), j->err, ASYNC_DUMP_THREADS); });
         return 0;
     }
     // write_once(): cor.cu:1033-1051 -- "x,y,z,ux,uy,uz" of every inlet / outlet node (labels 2,3,5,6,7), %f.
@@ -1715,6 +1736,10 @@ struct Solver final : SolverBase {
         int k = 0, tol_count = 0;
         const int max_batch = std::max(1, std::min(ACC_SLOTS - 2, 48));
         std::vector<double> S(ACC_SLOTS);
+        static const bool trace = getenv("LBM_TRACE") != nullptr;
+        double tr_step = 0, tr_fetch = 0, tr_save = 0;
+        auto now = []() { return std::chrono::steady_clock::now(); };
+        auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
         while (k <= max_it && tol_count <= stag_max) {
             // the loop cannot end by the tolerance rule in fewer than stag_max + 1 - tol_count more steps
             // (at most one hit per step), so a batch of that many never overshoots the stopping iteration
@@ -1726,6 +1751,7 @@ struct Solver final : SolverBase {
                     nb = j + 1;
                     break;
                 }
+            const auto tb0 = now();
             CK(cudaMemsetAsync(d_acc + 2, 0, sizeof(double) * nb, st));
             if (use_persist()) {  // the whole batch in one cooperative launch; moments of its last step (a save iteration, if any)
                 int r = persist_steps(nb, true, d_acc + 2);
@@ -1741,6 +1767,7 @@ struct Solver final : SolverBase {
             have_moments = true;
             CK(cudaMemcpyAsync(S.data(), d_acc + 2, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            tr_step += secs(tb0, now());
             for (int j = 0; j < nb; j++) {
                 float sum_next = (float)S[j];
                 residual = std::fabs(sum_next - sum_current) / sum_next;
@@ -1749,8 +1776,11 @@ struct Solver final : SolverBase {
                     std::cout << "ITERATION # " << k << ", collapse time: " << milli << " ms, residual:" << residual
                               << std::endl;
                     logfile << residual << std::endl;
+                    const auto tf0 = now();
                     int r = fetch_for_output();
+                    const auto tf1 = now();
                     if (!r) r = save_fetched_async(k);
+                    tr_fetch += secs(tf0, tf1), tr_save += secs(tf1, now());
                     if (r) return r;
                 }
                 k++;
@@ -1761,7 +1791,9 @@ struct Solver final : SolverBase {
         }
         float milli = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (write_files) {
-            int r = output_save(k);  // joins the dump in flight first
+            const auto tj0 = now();
+            int r = output_save(k);  // joins the dumps in flight first
+            if (trace) fprintf(stderr, "[lbm trace] run_converge: %d iterations, stepping %.1f ms, fetches %.1f ms, handing dumps over %.1f ms, final dump + joins %.1f ms\n", k, tr_step * 1e3, tr_fetch * 1e3, tr_save * 1e3, secs(tj0, now()) * 1e3);
             if (r) return r;
             std::cout << "TOTAL RUNNING TIME: " << milli << " MILLI SECONDS" << "#LATTICE" << compact_total << std::endl;
             std::cout << "Residual is " << residual << std::endl;

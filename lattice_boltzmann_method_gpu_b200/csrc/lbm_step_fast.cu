@@ -1,5 +1,6 @@
-// FAST arithmetic instantiation of the fused step (default nvcc FMA contraction).
-// This is the measured path.
+// FAST arithmetic instantiation of the fused step.  This is the measured path.  Built with -fmad=false
+// like the STRICT unit: the FAST collision fuses by explicit fma() calls (lattice.cuh), so its results do
+// not depend on which kernel variant ptxas happened to contract how.
 #include "step_dense.cuh"
 
 namespace lbm {

@@ -276,9 +276,8 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned gen) {
         }
         unsigned v;
         do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < gen);
-        __threadfence();
     }
     __syncthreads();
 }
@@ -293,6 +292,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
     const long long nwarps = (long long)gridDim.x * (PERSIST_BLOCK / 32);
     const int lane = threadIdx.x & 31;
     const long long first_chunk = sp.id_begin >> 5, end_chunk = (sp.id_end + 31) >> 5;
+    __shared__ double cta_sum[PERSIST_BLOCK / 32];
     for (int s = 0; s < pa.nsteps; s++) {
         const AaStep st{pa.moments_last && s == pa.nsteps - 1, pa.resid != 0};
         const T pulse = pa.pulse ? pa.pulse[s] : T(1.0);
@@ -306,7 +306,17 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
             for (long long seg = sp.seg_begin + warp0; seg < sp.seg_end; seg += nwarps)
                 aa_odd_record<T, STRICT, false, true>(sp, seg, st, pulse, velsum);
         }
-        if (st.resid) warp_add(pa.S + s, velsum);
+        if (st.resid) {  // one atomic per CTA and step: thousands of same-address atomics per step serialise in L2
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
+            if (lane == 0) cta_sum[threadIdx.x >> 5] = velsum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < PERSIST_BLOCK / 32; w++) t += cta_sum[w];
+                if (t != 0.0) atomicAdd(pa.S + s, t);
+            }
+        }
         if (s + 1 < pa.nsteps) grid_barrier(pa.barrier, (unsigned)(s + 1));
     }
 }
@@ -324,8 +334,11 @@ cudaError_t launch_sparse_aa_persist_impl(const SparseParams<T> &p_in, const Per
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     per_sm = std::min(per_sm, sizeof(T) == 8 ? 1 : 2);
     const long long work = std::max((p.id_end - p.id_begin + 31) / 32 + 1, p.seg_end - p.seg_begin);
-    long long blocks = std::min<long long>((long long)sm_count * per_sm, (work + PERSIST_BLOCK / 32 - 1) / (PERSIST_BLOCK / 32));
-    blocks = std::max<long long>(1, std::min<long long>(blocks, (long long)BAR_GROUP * 64));
+    // as many warps as give every warp the same number of rounds (an uneven last round makes everybody wait)
+    const long long wpb = PERSIST_BLOCK / 32, max_blocks = std::min<long long>((long long)sm_count * per_sm, (long long)BAR_GROUP * 64);
+    const long long rounds = std::max<long long>(1, (work + max_blocks * wpb - 1) / (max_blocks * wpb));
+    const long long warps = (work + rounds - 1) / rounds;
+    long long blocks = std::max<long long>(1, std::min(max_blocks, (warps + wpb - 1) / wpb));
     PersistArgs<T> a = pa;
     void *args[2] = {(void *)&p, (void *)&a};
     return cudaLaunchCooperativeKernel((const void *)k_sparse_aa_persist<T, STRICT>, dim3((unsigned)blocks), dim3(PERSIST_BLOCK), args, 0, s);

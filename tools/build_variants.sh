@@ -12,7 +12,7 @@ for v in "$@"; do
   extra=""
   [ -n "$SP64" ] && extra="$extra -DLBM_SP64_MINB=$SP64"
   [ -n "$SP32" ] && extra="$extra -DLBM_SP32_MINB=$SP32"
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC \
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC \
        -DLBM_F64_MINB=$1 -DLBM_F32_MINB=$2 $extra -c lbm_step_fast.cu -o /tmp/fast_$1_$2.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/liblbm_$1_$2.so \
        lbm_geo.o lbm_step_strict.o /tmp/fast_$1_$2.o lbm_api.o lbm_voxel.o -lcudart

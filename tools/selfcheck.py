@@ -31,7 +31,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "-DLBM_
 def build():
     OUT.mkdir(parents=True, exist_ok=True)
     objs = []
-    for name, fmad in (("lbm_geo", False), ("lbm_voxel", False), ("lbm_step_strict", False), ("lbm_step_fast", True), ("lbm_api", True)):
+    for name, fmad in (("lbm_geo", False), ("lbm_voxel", False), ("lbm_step_strict", False), ("lbm_step_fast", False), ("lbm_api", True)):
         o = OUT / f"{name}.o"
         cmd = ["nvcc", *FLAGS] + ([] if fmad else ["-fmad=false"]) + ["-c", str(SRC / f"{name}.cu"), "-o", str(o)]
         newest = max(p.stat().st_mtime for p in list(SRC.glob("*.cu*")) + list(SRC.glob("*.h")))

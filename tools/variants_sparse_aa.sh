@@ -9,7 +9,7 @@ mkdir -p ../../variants
 for v in "$@"; do
   set -- $v
   tag=$1_$2_$3_$4
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC \
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC \
        -DLBM_SPAA64_MINB=$1 -DLBM_SPAA64_ODD_MINB=$2 -DLBM_SPAA32_MINB=$3 -DLBM_SPAA32_ODD_MINB=$4 $EXTRA \
        -c lbm_step_fast.cu -o /tmp/fast_spaa_$tag.o
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/liblbm_spaa_$tag.so \
