@@ -301,6 +301,20 @@ int lbm_slab_step(lbm_handle h, int32_t n, int32_t flags_last, double *S_out, fl
 int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset);
 int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync);
 
+/* ---- mailboxes: the fused exchange of the dense in-place storage without mapping the population buffers ----
+ * cudaIpcOpenMemHandle costs 50-65 ms per GB of the allocation it maps (0.74 s for a 512^3 fp64 slab), and a
+ * neighbour only ever writes the 5 populations that cross the face.  lbm_mail_export(side) creates this slab's
+ * mailbox of that side -- 10 planes: the entering populations as its odd step pulls them from the halo plane and as
+ * its even step reads them in its outermost owned plane -- and publishes it like lbm_p2p_export publishes the
+ * buffers; lbm_mail_attach(side, the NEIGHBOUR's mailbox of the facing side as mapped here) switches that face over:
+ * the face launches read the entering populations from the own mailbox (base-pointer redirection, the kernel does
+ * not know) and store the leaving ones into the neighbour's.  Both slabs of a face switch together, between two
+ * steps; checkpoints and lbm_debug_get_populations see the complete population buffer (the mailbox is drained and
+ * re-filled around them).  LBM_STORE_DENSE_AA only. */
+int lbm_mail_export(lbm_handle h, int32_t side, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset, int64_t *stride,
+                    int64_t *guard);
+int lbm_mail_attach(lbm_handle h, int32_t side, void *peer_mail);
+
 /* ---- several z-slabs driven from ONE process: the multi-GPU form of the reference's main() ----
  * (SURVEY 8b `lbm_create_distributed`; the reference is single-GPU, ldc.cu:612-717.)
  * nslabs contiguous z ranges of desc's box, slab r on CUDA device devices[r] (NULL: r modulo the device

@@ -35,6 +35,12 @@ __host__ __device__ constexpr int oppq(int q) {
     constexpr int a[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
     return a[q];
 }
+// the 5 directions with c_z = +1 (and, same order, their counterparts with c_z = -1) numbered 0..4: slot of a
+// crossing population in a slab's mailbox
+__host__ __device__ constexpr int kslot(int q) {
+    constexpr int a[Q] = {-1, -1, -1, -1, -1, 0, 0, -1, -1, -1, -1, 1, 1, 2, 2, 3, 4, 3, 4};
+    return a[q];
+}
 __host__ __device__ constexpr int caxis(int q, int axis) { return axis == 0 ? cxq(q) : (axis == 1 ? cyq(q) : czq(q)); }
 
 // ---------------------------------------------------------------------------

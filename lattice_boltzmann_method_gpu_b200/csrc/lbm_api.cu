@@ -61,6 +61,8 @@ struct SolverBase {
     virtual int slab_steps(int n, int flags_last, double *S_out, float *ms) = 0;
     virtual int sync_export(lbm_ipc_handle *h, void **ptr, int64_t *boff) = 0;
     virtual int sync_attach(int side, void *peer_sync) = 0;
+    virtual int mail_export(int side, lbm_ipc_handle *h, void **ptr, int64_t *boff, int64_t *ms, int64_t *guard) = 0;
+    virtual int mail_attach(int side, void *peer_mail) = 0;
     virtual void set_inproc_neighbour(int side, SolverBase *nb) = 0;
     virtual cudaEvent_t face_event(int k) = 0;
     virtual int enqueue_step(int flags, double *acc_slot) = 0;  // begin + interior + end, no host sync
@@ -153,6 +155,10 @@ struct Solver final : SolverBase {
     // fused peer-to-peer halo exchange (per side: neighbour's two buffers, q stride, halo offset)
     T *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     long long peer_qs[2] = {0, 0}, peer_c0[2] = {0, 0}, peer_own[2] = {0, 0};
+    // mailboxes of the dense in-place storage (StepParams::mail): own ones per side, the neighbours' as mapped here
+    T *d_mail[2] = {nullptr, nullptr}, *peer_mail[2] = {nullptr, nullptr};
+    long long mail_ms = 0, mail_G = 0;
+    bool mail_live[2] = {false, false};  // the mailbox, not the population buffer, holds the current values of its slots
     // neighbour ordering of slab steps: flags in peer memory (other process) or events (same process)
     unsigned long long *d_sync = nullptr;               // [0] low neighbour's progress, [1] high neighbour's, [2] timeout
     unsigned long long *peer_sync[2] = {nullptr, nullptr};  // where this slab reports its own progress, per side
@@ -191,6 +197,7 @@ struct Solver final : SolverBase {
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
         fr(d_sid), fr(d_cmeta), fr(d_rec_links), fr(d_bcslot), fr(d_bclinks);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
+        fr(d_mail[0]), fr(d_mail[1]);
         fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count), fr(d_pulse), fr(d_barrier);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -554,6 +561,8 @@ struct Solver final : SolverBase {
     void detach_neighbours() {
         peer_sync[0] = peer_sync[1] = nullptr;
         inproc_nb[0] = inproc_nb[1] = nullptr;
+        peer_mail[0] = peer_mail[1] = nullptr;
+        mail_live[0] = mail_live[1] = false;
         sync_base = 0;
     }
 
@@ -740,6 +749,15 @@ struct Solver final : SolverBase {
         StepParams<T> p = make_params(c0, c1, acc);
         // face_sides bit 0: this range is the lowest owned plane, bit 1: the highest -> push to attached peers
         const int which = d_nxt == d_fa ? 0 : 1;
+        for (int sd = 0; sd < 2; sd++) {
+            if (!(face_sides & (1 << sd)) || !peer_mail[sd]) continue;
+            // the neighbour's mailbox: part A (its halo replica) on even steps, part B (its owned face plane) on odd ones
+            T *dst = peer_mail[sd] + (p.parity ? 5 * mail_ms : 0);
+            if (sd == 1) p.peer_up = dst, p.peer_up_qs = mail_ms, p.peer_up_c0 = mail_G, p.peer_up_own = mail_G;
+            else p.peer_dn = dst, p.peer_dn_qs = mail_ms, p.peer_dn_c0 = mail_G, p.peer_dn_own = mail_G;
+            p.peer_mail = 1, p.face_c0 = c0;
+            p.mail[sd] = d_mail[sd], p.mail_ms = mail_ms, p.mail_G = mail_G;
+        }
         if ((face_sides & 2) && peer_buf[1][which]) {
             p.peer_up = peer_buf[1][which], p.peer_up_qs = peer_qs[1], p.peer_up_c0 = peer_c0[1], p.peer_up_own = peer_own[1];
             p.face_c0 = sparse ? face_id0[1] : c0;
@@ -876,7 +894,7 @@ struct Solver final : SolverBase {
         if (in_step) FAIL(LBM_ERR_STATE, "lbm_step_begin called twice");
         CK(cudaSetDevice(d.device));
         const bool mom = flags & LBM_STEP_MOMENTS, res = flags & LBM_STEP_VELSUM;
-        if (in_place() && ((lo_halo && !peer_buf[0][0]) || (hi_halo && !peer_buf[1][0])))
+        if (in_place() && ((lo_halo && !peer_buf[0][0] && !peer_mail[0]) || (hi_halo && !peer_buf[1][0] && !peer_mail[1])))
             FAIL(LBM_ERR_STATE, "in-place storage exchanges slab faces by peer stores only: call lbm_p2p_attach first");
         step_flags = flags;
         step_acc = acc ? acc : d_acc, step_nosync = acc != nullptr;
@@ -896,7 +914,7 @@ struct Solver final : SolverBase {
         if (hi_halo) {
             const int sides = 2 | ((lo_halo && zb == zt) ? 1 : 0);
             if ((r = launch_range(plane_c(zt), plane_c(zt + 1), mom, res, step_acc, sides))) return r;
-            if (!peer_buf[1][0]) {
+            if (!fused(1)) {
                 if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[1], face_n[1], 1, d_send[1], face_n[1], st));
                 else CK(launch_halo_pack<T>(d_nxt, qstride, box, zt - box.z0, 1, d_send[1], st));
                 launches++;
@@ -907,7 +925,7 @@ struct Solver final : SolverBase {
             if ((r = launch_range(plane_c(zb), plane_c(zb + 1), mom, res, step_acc, 1))) return r;
             i0 = plane_c(zb + 1);
         }
-        if (lo_halo && !peer_buf[0][0]) {
+        if (lo_halo && !fused(0)) {
             if (sparse) CK(launch_halo_pack_sparse<T>(d_nxt, qstride, face_id0[0], face_n[0], 0, d_send[0], face_n[0], st));
             else CK(launch_halo_pack<T>(d_nxt, qstride, box, zb - box.z0, 0, d_send[0], st));
             launches++;
@@ -937,12 +955,12 @@ struct Solver final : SolverBase {
             int r = step_interior();
             if (r) return r;
         }
-        if (lo_halo && !peer_buf[0][0]) {
+        if (lo_halo && !fused(0)) {
             if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[0], halo_n[0], 0, d_recv[0], halo_n[0], st));
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, 0, 0, d_recv[0], st));
             launches++;
         }
-        if (hi_halo && !peer_buf[1][0]) {
+        if (hi_halo && !fused(1)) {
             if (sparse) CK(launch_halo_unpack_sparse<T>(d_nxt, qstride, d_labelc, fluid_label, halo_id0[1], halo_n[1], 1, d_recv[1], halo_n[1], st));
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
             launches++;
@@ -992,7 +1010,7 @@ struct Solver final : SolverBase {
         if (n < 0) FAIL(LBM_ERR_ARG, "negative step count");
         for (int sd = 0; sd < 2; sd++) {
             if (!(sd == 0 ? lo_halo : hi_halo)) continue;
-            if (!peer_buf[sd][0]) FAIL(LBM_ERR_STATE, "lbm_slab_step needs the fused peer-store exchange: lbm_p2p_attach side %d first", sd);
+            if (!peer_buf[sd][0] && !peer_mail[sd]) FAIL(LBM_ERR_STATE, "lbm_slab_step needs the fused peer-store exchange: lbm_p2p_attach side %d first", sd);
             if (!peer_sync[sd] && !inproc_nb[sd])
                 FAIL(LBM_ERR_STATE, "lbm_slab_step: no ordering with the neighbour on side %d (lbm_sync_attach)", sd);
         }
@@ -1020,6 +1038,81 @@ struct Solver final : SolverBase {
             CK(cudaStreamSynchronize(st));
         }
         return check_sync_error();
+    }
+    bool fused(int sd) const { return peer_buf[sd][0] != nullptr || peer_mail[sd] != nullptr; }
+    long long halo_cell0(int side) const { return side == 0 ? 0 : (long long)(box.z1 - box.z0 - 1) * box.plane; }
+    long long face_cell0(int side) const { return side == 0 ? plane_c(own_z0) : plane_c(own_z1 - 1); }
+    // move the slots of the entering directions between the population buffer and a side's mailbox
+    int mail_move(int side, int dir) {
+        CK(launch_mail_copy<T>(d_fa, qstride, d_mail[side], mail_ms, mail_G, face_cell0(side), halo_cell0(side), box.plane, side, dir, st));
+        launches++;
+        return 0;
+    }
+    // make the population buffer complete again (before it is read as a whole or the neighbours change)
+    int mail_drain() {
+        for (int sd = 0; sd < 2; sd++)
+            if (mail_live[sd]) {
+                int r = mail_move(sd, 1);
+                if (r) return r;
+                mail_live[sd] = false;
+            }
+        return 0;
+    }
+    int mail_refill() {
+        for (int sd = 0; sd < 2; sd++)
+            if (peer_mail[sd] && !mail_live[sd]) {
+                int r = mail_move(sd, 0);
+                if (r) return r;
+                mail_live[sd] = true;
+            }
+        return 0;
+    }
+    int mail_export(int side, lbm_ipc_handle *h, void **ptr, int64_t *boff, int64_t *ms, int64_t *guard) override {
+        if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
+        if (!have_init) FAIL(LBM_ERR_STATE, "mail_export before initialize");
+        if (d.storage != LBM_STORE_DENSE_AA) FAIL(LBM_ERR_STATE, "mailboxes exist for the dense in-place storage only");
+        if (!(side == 0 ? lo_halo : hi_halo)) FAIL(LBM_ERR_ARG, "no neighbour on side %d", side);
+        CK(cudaSetDevice(d.device));
+        mail_G = box.px + 32, mail_ms = box.plane + 2 * mail_G;
+        if (!d_mail[side]) {
+            if (dalloc(&d_mail[side], (size_t)mail_ms * 10)) return LBM_ERR_NOMEM;
+            CK(cudaMemsetAsync(d_mail[side], 0, (size_t)mail_ms * 10 * sizeof(T), st));
+        }
+        if (h) {
+            cudaIpcMemHandle_t ih;
+            CK(cudaIpcGetMemHandle(&ih, d_mail[side]));
+            memset(h, 0, sizeof(lbm_ipc_handle));
+            memcpy(h, &ih, sizeof ih);
+        }
+        if (ptr) *ptr = d_mail[side];
+        if (boff) {
+            int r = alloc_offset(d_mail[side], boff);
+            if (r) return r;
+        }
+        if (ms) *ms = mail_ms;
+        if (guard) *guard = mail_G;
+        return 0;
+    }
+    // peer_mail: the NEIGHBOUR's mailbox of the side facing this slab, as mapped here (null detaches).  From now on
+    // this slab reads the entering populations of that face from its own mailbox and stores the leaving ones into
+    // the neighbour's: both sides of a face must switch together, between two steps.
+    int mail_attach(int side, void *pm) override {
+        if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
+        if (!have_init || (pm && !d_mail[side])) FAIL(LBM_ERR_STATE, "lbm_mail_attach before lbm_mail_export of that side");
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(st));
+        if (pm && !mail_live[side]) {
+            int r = mail_move(side, 0);
+            if (r) return r;
+            mail_live[side] = true;
+        } else if (!pm && mail_live[side]) {
+            int r = mail_move(side, 1);
+            if (r) return r;
+            mail_live[side] = false;
+        }
+        peer_mail[side] = (T *)pm;
+        CK(cudaStreamSynchronize(st));
+        return 0;
     }
     int sync_export(lbm_ipc_handle *h, void **ptr, int64_t *boff) override {
         CK(cudaSetDevice(d.device));
@@ -1108,6 +1201,10 @@ struct Solver final : SolverBase {
         if (in_step) FAIL(LBM_ERR_STATE, "checkpoint inside lbm_step_begin / lbm_step_end");
         if (!path) FAIL(LBM_ERR_ARG, "null path");
         CK(cudaSetDevice(d.device));
+        {
+            int r = mail_drain();  // the population buffer is complete again; mail_refill() below hands the slots back
+            if (r) return r;
+        }
         CK(cudaStreamSynchronize(st));
         // the buffer the next step pulls from holds the whole state (the other one is overwritten),
         // except for the never-rewritten static slots, which initialize() put into both
@@ -1126,6 +1223,10 @@ struct Solver final : SolverBase {
         FILE *f = nullptr;
         int rc = 0;
         auto done = [&](int code, const std::string &msg) {
+            if (have_init) {  // hand the mailbox slots back whatever happened to the file
+                const int r2 = mail_refill();
+                if (!code) code = r2;
+            }
             if (f) fclose(f);
             for (auto &e : evh)
                 if (e) cudaEventDestroy(e);
@@ -1349,6 +1450,14 @@ struct Solver final : SolverBase {
     int get_populations(void *f) override {
         if (!have_init) FAIL(LBM_ERR_STATE, "get_populations before initialize");
         CK(cudaSetDevice(d.device));
+        {
+            int r = mail_drain();
+            if (r) return r;
+        }
+        struct Refill {
+            Solver *s;
+            ~Refill() { s->mail_refill(); }
+        } refill{this};
         const size_t n = (size_t)stored_own;
         if (d.storage == LBM_STORE_SPARSE_AA) {
             T *tmp = nullptr;
@@ -2081,6 +2190,12 @@ int lbm_sync_export(lbm_handle h, lbm_ipc_handle *handle, void **ptr, int64_t *b
     H_OR_FAIL;
     return h->s->sync_export(handle, ptr, byte_offset);
 }
+int lbm_mail_export(lbm_handle h, int32_t side, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset, int64_t *stride,
+                    int64_t *guard) {
+    H_OR_FAIL;
+    return h->s->mail_export(side, handle, ptr, byte_offset, stride, guard);
+}
+int lbm_mail_attach(lbm_handle h, int32_t side, void *peer_mail) { H_OR_FAIL; return h->s->mail_attach(side, peer_mail); }
 int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync) { H_OR_FAIL; return h->s->sync_attach(side, peer_sync); }
 int lbm_set_option(lbm_handle h, const char *name, double value) { H_OR_FAIL; return name ? h->s->set_option(name, value) : LBM_ERR_ARG; }
 int lbm_debug_selfcheck(lbm_handle h, uint64_t out[3]) { H_OR_FAIL; return out ? h->s->selfcheck(out) : LBM_ERR_ARG; }

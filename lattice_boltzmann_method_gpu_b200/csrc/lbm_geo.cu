@@ -982,6 +982,31 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
     return cudaGetLastError();
 }
 
+// ---- mailboxes of the dense in-place storage (StepParams::mail): copy the slots of the 5 entering directions
+// between the population buffer and a side's mailbox
+template <typename T>
+__global__ void k_mail_copy(T *a, long long qs, T *mail, long long ms, long long G, long long face_c0, long long halo_c0,
+                            long long plane, int side, int dir) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= plane) return;
+#pragma unroll
+    for (int q = 1; q < Q; q++) {
+        if (czq(q) != (side == 0 ? 1 : -1)) continue;
+        T *mA = mail + (long long)kslot(q) * ms + G + i, *mB = mail + (long long)(5 + kslot(q)) * ms + G + i;
+        T *pA = a + (long long)oppq(q) * qs + halo_c0 + i, *pB = a + (long long)q * qs + face_c0 + i;
+        if (dir == 0) *mA = *pA, *mB = *pB;
+        else *pA = *mA, *pB = *mB;
+    }
+}
+template <typename T>
+cudaError_t launch_mail_copy(T *a, long long qstride, T *mail, long long ms, long long G, long long face_c0, long long halo_c0,
+                             long long plane, int side, int dir, cudaStream_t s) {
+    k_mail_copy<T><<<nblocks(plane, 256), 256, 0, s>>>(a, qstride, mail, ms, G, face_c0, halo_c0, plane, side, dir);
+    return cudaGetLastError();
+}
+template cudaError_t launch_mail_copy<float>(float *, long long, float *, long long, long long, long long, long long, long long, int, int, cudaStream_t);
+template cudaError_t launch_mail_copy<double>(double *, long long, double *, long long, long long, long long, long long, long long, int, int, cudaStream_t);
+
 // ---- neighbour handshake between z-slabs that live in different processes (one process per GPU)
 // A slab may start the face launches of step t+1 only after both neighbours finished the face launches of
 // step t (they read the halo plane this slab is about to overwrite, and wrote the one it is about to read).

@@ -77,6 +77,17 @@ struct StepParams {
     long long peer_up_c0, peer_dn_c0;   // offset of its halo plane (cells, or compact ids for sparse)
     long long peer_up_own, peer_dn_own; // offset of its outermost owned plane (AA odd step pushes there)
     long long face_c0;              // offset of this launch's plane (cell of c_begin / first compact id)
+    // Mailboxes (dense in-place storage across processes): the 5 populations that cross a face live in a small
+    // separate allocation per side instead of in the halo / face planes of the population buffer, so that a
+    // neighbour maps ~80 MB instead of the whole buffer (cudaIpcOpenMemHandle costs ~50-65 ms per GB).
+    //   part A [5][mail_ms]: slot opp(q) of the HALO-plane cells  (written by the neighbour's even step and by this
+    //                        slab's boundary links there, read by this slab's odd step)
+    //   part B [5][mail_ms]: slot q of this slab's outermost OWNED plane  (written by the neighbour's odd step and by
+    //                        this slab's boundary links, read by this slab's even step)
+    // for the 5 directions q that enter through that face; element G + (in-plane cell index).
+    T *mail[2];                     // this slab's own mailboxes (low / high side) when the launch covers that face, else null
+    long long mail_ms, mail_G;
+    int peer_mail;                  // peer_up / peer_dn point at the neighbour's mailbox (part A on even, part B on odd steps)
     // per-direction base pointers of the dense kernels, so that an access is base[q] + c (one 64-bit
     // add) instead of five integer instructions: pull_base[q][c] is the population direction q pulls
     // for cell c, store_base[q][c] the slot its post-collision value goes to (storage mode folded in)
@@ -156,6 +167,10 @@ template <typename T>
 cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, int fluid_label, Box box, int zl, int side,
                                const T *buf, cudaStream_t s);
 
+// mailbox <-> population buffer (dir 0: fill the mailbox from the buffer, 1: drain it back); see StepParams::mail
+template <typename T>
+cudaError_t launch_mail_copy(T *a, long long qstride, T *mail, long long ms, long long G, long long face_c0, long long halo_c0,
+                             long long plane, int side, int dir, cudaStream_t s);
 // neighbour handshake of z-slabs in different processes (flags in peer memory), lbm_geo.cu
 cudaError_t launch_slab_wait(unsigned long long *sync, unsigned long long need_lo, unsigned long long need_hi,
                              unsigned long long timeout_ns, cudaStream_t s);

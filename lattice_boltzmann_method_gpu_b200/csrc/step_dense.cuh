@@ -262,6 +262,14 @@ __device__ __forceinline__ void push_to_peers(const StepParams<T> &p, long long 
         T *peer = czq(q) > 0 ? p.peer_up : p.peer_dn;
         if (!peer) continue;
         const long long qs = czq(q) > 0 ? p.peer_up_qs : p.peer_dn_qs;
+        if (p.peer_mail) {  // the neighbour's mailbox: part A on even steps, part B (shifted in-plane target) on odd ones
+            if (MODE == MODE_AA_EVEN) {
+                peer[(long long)kslot(q) * qs + (czq(q) > 0 ? p.peer_up_c0 : p.peer_dn_c0) + i] = f[q];
+            } else if (MODE == MODE_AA_ODD && !(node & (1u << oppq(q)))) {
+                peer[(long long)kslot(q) * qs + (czq(q) > 0 ? p.peer_up_own : p.peer_dn_own) + i + cxq(q) + (long long)p.box.px * cyq(q)] = f[q];
+            }
+            continue;
+        }
         if (MODE == MODE_AB) {
             peer[(long long)q * qs + (czq(q) > 0 ? p.peer_up_c0 : p.peer_dn_c0) + i] = f[q];
         } else if (MODE == MODE_AA_EVEN) {
@@ -425,6 +433,23 @@ void set_bases(StepParams<T> &p) {
         p.pull_base[q] = p.src + pull_index<MODE>(q, 0, p.qstride, off);
         p.store_base[q] = p.dst + store_index<MODE>(q, 0, p.qstride, off);
         p.slot_base[q] = p.dst + slot_index<MODE>(q, 0, p.qstride, off);
+    }
+    // mailboxes of the faces this launch covers: the slots of the 5 entering directions live there
+    for (int side = 0; side < 2; side++) {
+        if (!p.mail[side] || MODE == MODE_AB) continue;
+        for (int q = 1; q < Q; q++) {
+            if (czq(q) != (side == 0 ? 1 : -1)) continue;  // enters through the low face with c_z = +1, through the high one with -1
+            const long long inpl = (long long)cxq(q) + (long long)p.box.px * cyq(q);
+            T *A = p.mail[side] + (long long)kslot(q) * p.mail_ms + p.mail_G - p.face_c0;
+            T *B = p.mail[side] + (long long)(5 + kslot(q)) * p.mail_ms + p.mail_G - p.face_c0;
+            if (MODE == MODE_AA_EVEN) {
+                p.pull_base[q] = B;          // a[q][c]: pushed here by the neighbour's odd step / this node's boundary link
+                p.slot_base[q] = A - inpl;   // a[opp q][c - off_q]: the halo cell's slot, read by the odd step
+            } else {
+                p.pull_base[q] = A - inpl;   // a[opp q][c - off_q]
+                p.slot_base[q] = B;          // a[q][c]
+            }
+        }
     }
 }
 

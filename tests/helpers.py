@@ -201,9 +201,17 @@ def rel_err(got, ref):
     return max(e_u / scale, e_r)
 
 
-def attach_virtual_slabs(cs):
+def attach_virtual_slabs(cs, mail=False):
     """several slab handles on ONE GPU: every handle stores its crossing populations straight into its
-    neighbours' buffers (lbm_p2p_attach with plain device pointers)"""
+    neighbours' buffers (lbm_p2p_attach with plain device pointers) or, mail=True, into their mailboxes
+    (lbm_mail_export / lbm_mail_attach, dense in-place storage)"""
+    if mail:
+        boxes = [{s: c.mail_export(s)["ptr"] for s, nb in ((0, r - 1), (1, r + 1)) if 0 <= nb < len(cs)} for r, c in enumerate(cs)]
+        for r, c in enumerate(cs):
+            for side, nb in ((0, r - 1), (1, r + 1)):
+                if 0 <= nb < len(cs):
+                    c.mail_attach(side, boxes[nb][1 - side])
+        return
     exp = [c.p2p_export() for c in cs]
     for r, c in enumerate(cs):
         for side, nb in ((0, r - 1), (1, r + 1)):
