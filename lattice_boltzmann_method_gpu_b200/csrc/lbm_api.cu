@@ -810,9 +810,10 @@ struct Solver final : SolverBase {
 #ifdef LBM_SELFCHECK
         return false;  // the shadow tags are per launch: a launch must be one step
 #endif
-        if (opt_persist >= 0) return opt_persist != 0;
-        // one buffer of 19 directions; below ~half the 126 MB L2 every step is served from L2
-        return (size_t)qstride * Q * sizeof(T) <= (size_t)64 << 20;
+        // opt-in (lbm_set_option("persistent", 1)): measured on the reference's 64^3 configurations one launch per
+        // step is as fast or faster (10.1 vs 12.2 us per step, profiles/r02_notes.md section 5) -- the grid barrier
+        // costs what the launch gap saves
+        return opt_persist > 0;
     }
     // n <= PERSIST_MAX_STEPS steps in one cooperative launch; S_dev: n device slots receiving sum|u| per step, or null
     int persist_steps(int n, bool moments_last, double *S_dev) {
@@ -1866,8 +1867,8 @@ struct Solver final : SolverBase {
                 int r = persist_steps(nb, true, d_acc + 2);
                 if (r) return r;
             } else {
-                for (int j = 0; j < nb; j++) {
-                    int r = launch_range(plane_c(own_z0), plane_c(own_z1), true, true, d_acc + 2 + j);
+                for (int j = 0; j < nb; j++) {  // moments are needed from the last step of a batch only (a save iteration, if any)
+                    int r = launch_range(plane_c(own_z0), plane_c(own_z1), j == nb - 1, true, d_acc + 2 + j);
                     if (r) return r;
                     std::swap(d_cur, d_nxt);
                     steps++;

@@ -213,10 +213,21 @@ __device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long lo
     if (st.resid) velsum += (double)(T)sqrt((double)(ux * ux + uy * uy + uz * uz));
 }
 
-__device__ __forceinline__ void warp_add(double *dst, double v) {
+// sum|u| of a CTA into one atomic: on a small grid thousands of same-address atomics per step serialise in L2
+// and cost more than the step itself.  Every thread of the CTA must call this.
+template <int NWARPS>
+__device__ __forceinline__ void cta_add(double *dst, double v) {
+    __shared__ double ws[NWARPS];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) t += ws[w];
+        if (t != 0.0) atomicAdd(dst, t);
+    }
 }
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
@@ -225,17 +236,17 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB
     const long long i = sp.id_begin + (long long)blockIdx.x * SPARSE_BLOCK + threadIdx.x;
     double velsum = 0.0;
     aa_even_node<T, STRICT, PEERS, false>(sp, i, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
-    if (RESID) warp_add(sp.base.resid, velsum);
+    if (RESID) cta_add<SPARSE_BLOCK / 32>(sp.base.resid, velsum);
 }
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
 __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_MINB : LBM_SPAA32_ODD_MINB)
     k_sparse_aa_odd(const __grid_constant__ SparseParams<T> sp) {
     const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
-    if (seg >= sp.seg_end) return;  // warp-uniform
     double velsum = 0.0;
-    aa_odd_record<T, STRICT, PEERS, false>(sp, seg, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
-    if (RESID) warp_add(sp.base.resid, velsum);
+    if (seg < sp.seg_end)  // warp-uniform
+        aa_odd_record<T, STRICT, PEERS, false>(sp, seg, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
+    if (RESID) cta_add<SPARSE_BLOCK / 32>(sp.base.resid, velsum);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -292,7 +303,6 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
     const long long nwarps = (long long)gridDim.x * (PERSIST_BLOCK / 32);
     const int lane = threadIdx.x & 31;
     const long long first_chunk = sp.id_begin >> 5, end_chunk = (sp.id_end + 31) >> 5;
-    __shared__ double cta_sum[PERSIST_BLOCK / 32];
     for (int s = 0; s < pa.nsteps; s++) {
         const AaStep st{pa.moments_last && s == pa.nsteps - 1, pa.resid != 0};
         const T pulse = pa.pulse ? pa.pulse[s] : T(1.0);
@@ -306,17 +316,7 @@ __global__ void __launch_bounds__(PERSIST_BLOCK, sizeof(T) == 8 ? 1 : 2)
             for (long long seg = sp.seg_begin + warp0; seg < sp.seg_end; seg += nwarps)
                 aa_odd_record<T, STRICT, false, true>(sp, seg, st, pulse, velsum);
         }
-        if (st.resid) {  // one atomic per CTA and step: thousands of same-address atomics per step serialise in L2
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) velsum += __shfl_xor_sync(0xffffffffu, velsum, o);
-            if (lane == 0) cta_sum[threadIdx.x >> 5] = velsum;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double t = 0.0;
-                for (int w = 0; w < PERSIST_BLOCK / 32; w++) t += cta_sum[w];
-                if (t != 0.0) atomicAdd(pa.S + s, t);
-            }
-        }
+        if (st.resid) cta_add<PERSIST_BLOCK / 32>(pa.S + s, velsum);
         if (s + 1 < pa.nsteps) grid_barrier(pa.barrier, (unsigned)(s + 1));
     }
 }
