@@ -1651,37 +1651,46 @@ struct Solver final : SolverBase {
         // z-planes are formatted by several host threads into their own buffers and written in order.
         const int nzp = z1 - z0;
         const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), max_threads, nzp}));
-        auto put = [](std::string &buf, auto v) { vtk_put(buf, v); };
-        // kind 0: density, 1: pressure, 2: velocity
-        auto format_planes = [&](int kind, std::vector<std::string> &parts) {
-            parts.assign((size_t)nthr, std::string());
+        // kind 0: density, 1: pressure, 2: velocity.  A value takes at most 15 characters with its blank
+        // ("-1.23457e-308 "), so a part's buffer is sized for the worst case and never grows; only the pages
+        // that are written become resident.
+        struct Part {
+            std::unique_ptr<char[]> data;
+            size_t len = 0;
+        };
+        auto format_planes = [&](int kind, std::vector<Part> &parts) {
+            parts.clear();
+            parts.resize((size_t)nthr);
             auto work = [&](int t) {
                 const int za = z0 + (int)((long long)nzp * t / nthr), zb = z0 + (int)((long long)nzp * (t + 1) / nthr);
-                std::string &buf = parts[(size_t)t];
-                buf.reserve((size_t)(x1 - x0) * (y1 - y0) * (zb - za) * (kind == 2 ? 36 : 12) + 64);
+                Part &part = parts[(size_t)t];
+                part.data.reset(new char[(size_t)(x1 - x0) * (y1 - y0) * (zb - za) * (kind == 2 ? 45 : 15) + VTK_MAX_CHARS]);
+                char *p = part.data.get();
                 for (int z = za; z < zb; z++)
                     for (int y = y0; y < y1; y++)
                         for (int x = x0; x < x1; x++) {
                             const int i = idx_of(x, y, z);
-                            if (kind == 0) put(buf, i >= 0 ? (float)prho[i] * C_rho : 0.0f);
+                            if (kind == 0) p = vtk_write(p, i >= 0 ? (float)prho[i] * C_rho : 0.0f);
                             else if (kind == 1) {
-                                if (i >= 0) put(buf, (float)prho[i] * C_pre / 3.0);  // double, as in cor.cu:983
-                                else put(buf, 0.0f);
+                                if (i >= 0) p = vtk_write(p, (float)prho[i] * C_pre / 3.0);  // double, as in cor.cu:983
+                                else p = vtk_write(p, 0.0f);
                             } else if (i >= 0) {
-                                put(buf, (float)pux[i] * C_U), put(buf, (float)puy[i] * C_U), put(buf, (float)puz[i] * C_U);
+                                p = vtk_write(p, (float)pux[i] * C_U), p = vtk_write(p, (float)puy[i] * C_U);
+                                p = vtk_write(p, (float)puz[i] * C_U);
                             } else {
-                                buf += "0 0 0 ";
+                                std::memcpy(p, "0 0 0 ", 6), p += 6;
                             }
                         }
+                part.len = (size_t)(p - part.data.get());
             };
             std::vector<std::thread> pool;
             for (int t = 1; t < nthr; t++) pool.emplace_back(work, t);
             work(0);
             for (auto &th : pool) th.join();
         };
-        std::vector<std::string> parts;
+        std::vector<Part> parts;
         auto flush = [&]() {
-            for (auto &s : parts) ofs.write(s.data(), (std::streamsize)s.size());
+            for (auto &s : parts) ofs.write(s.data.get(), (std::streamsize)s.len);
         };
         if (d.case_rule == LBM_CASE_GEO_OPENINGS) {
             ofs << "SCALARS DENSITY float\nLOOKUP_TABLE default\n";
