@@ -779,6 +779,7 @@ struct Solver final : SolverBase {
                 sp.cartc = d_cart, sp.cmeta = d_cmeta, sp.rec_links = d_rec_links, sp.bcslot = d_bcslot, sp.bclinks = d_bclinks;
                 sp.id_begin = sid_plane_first[(size_t)(c0 / box.plane)], sp.id_end = sid_plane_first[(size_t)(c1 / box.plane)];
                 sp.halo_lo_n = (int)halo_n[0], sp.halo_hi0 = (int)halo_id0[1];
+                sp.pdl = opt_pdl && !lo_halo && !hi_halo;
                 if (sp.base.parity == 0 ? sp.id_end <= sp.id_begin : sp.seg_end <= sp.seg_begin) return 0;
                 if (d.math == LBM_MATH_STRICT) CK(launch_step_sparse_aa_strict<T>(sp, moments, resid, st));
                 else CK(launch_step_sparse_aa_fast<T>(sp, moments, resid, st));
@@ -805,6 +806,7 @@ struct Solver final : SolverBase {
     int sm_count = 0;
     static constexpr int PERSIST_MAX_STEPS = 2048, PERSIST_BAR_WORDS = 64 + 32 * 64;  // = BAR_WORDS of step_sparse_aa.cuh
     int opt_persist = -1;  // lbm_set_option("persistent", 0 / 1); -1: by size
+    int opt_pdl = 1;       // lbm_set_option("overlap_launches", 0 / 1)
     bool use_persist() {
         if (d.storage != LBM_STORE_SPARSE_AA || lo_halo || hi_halo) return false;
 #ifdef LBM_SELFCHECK
@@ -1951,6 +1953,7 @@ struct Solver final : SolverBase {
     }
     int set_option(const char *name, double value) override {
         if (!strcmp(name, "persistent")) opt_persist = value < 0 ? -1 : (value != 0.0);
+        else if (!strcmp(name, "overlap_launches")) opt_pdl = value != 0.0;
         else FAIL(LBM_ERR_ARG, "unknown option '%s'", name);
         return 0;
     }

@@ -240,6 +240,7 @@ struct SparseParams {
     long long id_begin, id_end;  // compact ids of the even (local) step's launch
     int halo_lo_n, halo_hi0;     // local ids < halo_lo_n lie in the low halo plane, ids >= halo_hi0 in the high one
     int dk[Q];                   // (k - opp k) * qstride: from the array of opp(k) to the same node's slot in the array of k
+    int pdl;                     // launch with programmatic stream serialization (step_sparse_aa.cuh)
 };
 
 // fused step (lbm_step_fast.cu / lbm_step_strict.cu)

@@ -94,6 +94,14 @@ __device__ __forceinline__ void own_slot_bc(const SparseParams<T> &sp, long long
     }
 }
 
+// Programmatic dependent launch: a step kernel lets the next launch of the stream start as soon as all of its
+// own CTAs are resident (grid_dep_launch, first instruction), and waits for the previous launch to be complete
+// and visible only where it first touches populations (grid_dep_wait) -- geometry words, records and link
+// lists are never written by a step, so their loads and the launch latency itself (2 - 3 us, a third of a
+// 64^3 step) overlap the previous step's tail.  Both are no-ops when the launch does not carry the attribute.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // per-step switches that are template parameters of the one-step kernels and run-time values of the
 // persistent one
 struct AaStep {
@@ -109,14 +117,15 @@ __device__ __forceinline__ void aa_even_node(const SparseParams<T> &sp, long lon
     uint2 cm = make_uint2(0u, 0u);
     if (i < sp.id_end) cm = sp.cmeta[i >> 5];
     if (!((cm.x >> (i & 31)) & 1u)) return;
+    uint32_t node = 0u, rest = 0u;  // rest: links that are neither fluid-fed nor walls: inlet / outlet / static
+    if (cm.y) node = sp.nodec[i];
+    if (!CG) grid_dep_wait();
     T f[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) {
         LBM_CHK(p, p.pull_base[q] + i);
         f[q] = ld_pop<CG>(p.pull_base[q] + i);
     }
-    uint32_t node = 0u, rest = 0u;  // rest: links that are neither fluid-fed nor walls: inlet / outlet / static
-    if (cm.y) node = sp.nodec[i];
     if ((node & NODE_LINKS) && !(node & NODE_WALLS_ONLY)) rest = node & NODE_LINKS & ~sp.wallc[i];
     T rho, ux, uy, uz;
     collide_bgk<T, STRICT>(f, p.tau, p.inv_tau, rho, ux, uy, uz);
@@ -169,6 +178,7 @@ __device__ __forceinline__ void aa_odd_record(const SparseParams<T> &sp, long lo
         j[r] = b + lane;
     }
     if (!active) return;
+    if (!CG) grid_dep_wait();
     // ONE element index per direction, used for the load and for the store: inside the array of opp(k),
     // either the source's id or -- for a link -- this node's own slot in the array of k, which lies
     // dk[k] = (k - opp k) * qstride elements away
@@ -233,6 +243,7 @@ __device__ __forceinline__ void cta_add(double *dst, double v) {
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
 __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB : LBM_SPAA32_MINB)
     k_sparse_aa_even(const __grid_constant__ SparseParams<T> sp) {
+    grid_dep_launch();
     const long long i = sp.id_begin + (long long)blockIdx.x * SPARSE_BLOCK + threadIdx.x;
     double velsum = 0.0;
     aa_even_node<T, STRICT, PEERS, false>(sp, i, AaStep{MOMENTS, RESID}, sp.base.pulse_scale, velsum);
@@ -242,6 +253,7 @@ __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_MINB
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
 __global__ void __launch_bounds__(SPARSE_BLOCK, sizeof(T) == 8 ? LBM_SPAA64_ODD_MINB : LBM_SPAA32_ODD_MINB)
     k_sparse_aa_odd(const __grid_constant__ SparseParams<T> sp) {
+    grid_dep_launch();
     const long long seg = sp.seg_begin + (long long)blockIdx.x * (SPARSE_BLOCK / 32) + (threadIdx.x >> 5);
     double velsum = 0.0;
     if (seg < sp.seg_end)  // warp-uniform
@@ -346,17 +358,23 @@ cudaError_t launch_sparse_aa_persist_impl(const SparseParams<T> &p_in, const Per
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool PEERS>
 cudaError_t launch_sparse_aa_mode(const SparseParams<T> &p, cudaStream_t s) {
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(SPARSE_BLOCK), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+    cfg.attrs = at, cfg.numAttrs = (!PEERS && p.pdl) ? 1 : 0;
     if (p.base.parity == 0) {
         const long long n = p.id_end - p.id_begin;
         if (n <= 0) return cudaSuccess;
-        k_sparse_aa_even<T, STRICT, MOMENTS, RESID, PEERS><<<(unsigned)((n + SPARSE_BLOCK - 1) / SPARSE_BLOCK), SPARSE_BLOCK, 0, s>>>(p);
-    } else {
-        const long long nrec = p.seg_end - p.seg_begin;
-        if (nrec <= 0) return cudaSuccess;
-        const int wpb = SPARSE_BLOCK / 32;
-        k_sparse_aa_odd<T, STRICT, MOMENTS, RESID, PEERS><<<(unsigned)((nrec + wpb - 1) / wpb), SPARSE_BLOCK, 0, s>>>(p);
+        cfg.gridDim = dim3((unsigned)((n + SPARSE_BLOCK - 1) / SPARSE_BLOCK));
+        return cudaLaunchKernelEx(&cfg, k_sparse_aa_even<T, STRICT, MOMENTS, RESID, PEERS>, p);
     }
-    return cudaGetLastError();
+    const long long nrec = p.seg_end - p.seg_begin;
+    if (nrec <= 0) return cudaSuccess;
+    const int wpb = SPARSE_BLOCK / 32;
+    cfg.gridDim = dim3((unsigned)((nrec + wpb - 1) / wpb));
+    return cudaLaunchKernelEx(&cfg, k_sparse_aa_odd<T, STRICT, MOMENTS, RESID, PEERS>, p);
 }
 
 template <typename T, bool STRICT>

@@ -1,6 +1,6 @@
 """One small case, a few launches: the thing to put under ncu when a 64^3 step is slower than it should be.
 
-  python tools/small_case.py [--case ldc|pos|bif] [--n 64] [--precision f32] [--storage sparse_aa] [--persistent -1|0|1]
+  python tools/small_case.py [--case ldc|pos|bif] [--n 64] [--precision f32] [--storage sparse_aa] [--persistent -1|0|1] [--overlap 0|1]
                              [--steps 20] [--calls 3]
 MEASUREMENT INFRASTRUCTURE."""
 import argparse
@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--persistent", type=int, default=-1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--calls", type=int, default=3)
+    ap.add_argument("--overlap", type=int, default=-1, help="lbm_set_option('overlap_launches'): 0 / 1")
     a = ap.parse_args()
     import helpers as H  # case builders only
 
@@ -29,10 +30,12 @@ def main():
     H.gpu_setup(c, a.case)
     if a.persistent >= 0:
         c.set_option("persistent", a.persistent)
+    if a.overlap >= 0:
+        c.set_option("overlap_launches", a.overlap)
     c.step(a.steps)
     for _ in range(a.calls):
         ms = c.step_timed(a.steps)
-        print(f"{a.case} {a.precision} {a.storage} persistent={a.persistent}: {ms / a.steps * 1e3:.2f} us/step, "
+        print(f"{a.case} {a.precision} {a.storage} persistent={a.persistent} overlap={a.overlap}: {ms / a.steps * 1e3:.2f} us/step, "
               f"{c.num_fluid * a.steps / (ms * 1e-3) / 1e6:.0f} MLUPS", flush=True)
 
 
