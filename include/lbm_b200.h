@@ -344,7 +344,10 @@ int lbm_group_run_converge(lbm_group g, int32_t max_it, double tol, int32_t stag
 
 /* Tuning knobs that are not part of a case description.  "persistent": 1 runs batches of steps of the in-place
  * sparse storage in one cooperative launch with a grid barrier between steps (for grids that live in L2); 0 or
- * -1 (the default): one launch per step, which measured as fast or faster on the reference's 64^3 cases. */
+ * -1 (the default): one launch per step, which measured as fast or faster on the reference's 64^3 cases.
+ * "overlap_launches": 1 (default) launches the step kernels of the in-place storages with programmatic stream
+ * serialization, so that a step's launch latency and geometry loads overlap the previous step's tail (a 64^3
+ * step: 9.9 -> 7.6 us); 0 serialises launches the ordinary way.  Single-domain handles only. */
 int lbm_set_option(lbm_handle h, const char *name, double value);
 
 /* Self-checking build of the library (-DLBM_SELFCHECK; tools/selfcheck.py builds and runs it -- the stand-in for

@@ -720,6 +720,7 @@ struct Solver final : SolverBase {
         p.rho = d_rho, p.ux = d_ux, p.uy = d_uy, p.uz = d_uz;
         p.resid = acc;
         p.box = box, p.c_begin = c0, p.c_end = c1;
+        p.pdl = opt_pdl && !lo_halo && !hi_halo && in_place();  // single domain only: slab launches alternate with flag kernels
         p.fluid_label = fluid_label;
         p.tau = (T)d.tau;
         p.inv_tau = T(1.0) / p.tau;
@@ -779,7 +780,7 @@ struct Solver final : SolverBase {
                 sp.cartc = d_cart, sp.cmeta = d_cmeta, sp.rec_links = d_rec_links, sp.bcslot = d_bcslot, sp.bclinks = d_bclinks;
                 sp.id_begin = sid_plane_first[(size_t)(c0 / box.plane)], sp.id_end = sid_plane_first[(size_t)(c1 / box.plane)];
                 sp.halo_lo_n = (int)halo_n[0], sp.halo_hi0 = (int)halo_id0[1];
-                sp.pdl = opt_pdl && !lo_halo && !hi_halo;
+                sp.pdl = sp.base.pdl;
                 if (sp.base.parity == 0 ? sp.id_end <= sp.id_begin : sp.seg_end <= sp.seg_begin) return 0;
                 if (d.math == LBM_MATH_STRICT) CK(launch_step_sparse_aa_strict<T>(sp, moments, resid, st));
                 else CK(launch_step_sparse_aa_fast<T>(sp, moments, resid, st));

@@ -88,6 +88,7 @@ struct StepParams {
     T *mail[2];                     // this slab's own mailboxes (low / high side) when the launch covers that face, else null
     long long mail_ms, mail_G;
     int peer_mail;                  // peer_up / peer_dn point at the neighbour's mailbox (part A on even, part B on odd steps)
+    int pdl;                        // in-place storages: launch with programmatic stream serialization (step_dense.cuh)
     // per-direction base pointers of the dense kernels, so that an access is base[q] + c (one 64-bit
     // add) instead of five integer instructions: pull_base[q][c] is the population direction q pulls
     // for cell c, store_base[q][c] the slot its post-collision value goes to (storage mode folded in)

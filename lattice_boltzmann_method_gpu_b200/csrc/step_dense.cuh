@@ -205,6 +205,16 @@ constexpr int default_cfg() {
     return sizeof(T) == 8 ? 2 : 3;
 }
 
+// Loads of the speculative pull.  They have to be ISSUED before the thread knows whether it needs them, and
+// ptxas sinks an ordinary ld.global (also .nc, also from `asm volatile`) below the early exit that depends on
+// the segment byte -- which puts a dependent L2 round trip in front of every population load (SASS of round 1
+// and 2: `LDG.U8 kind ... @!P0 EXIT ; LDG ...`).  A relaxed gpu-scope load must be performed where it
+// stands; it is served by L2 like every streaming load of this kernel (in-place storage: 0.975 -> 0.983 fp64).
+#ifndef LBM_SPEC_LD
+#define LBM_SPEC_LD 1
+#endif
+// two-buffer storage: the read-only path, sunk or not, measured better than the relaxed load (0.954 / 0.890
+// against 0.948 / 0.885 of peak, fp64 / fp32)
 __device__ __forceinline__ double ld_spec(const double *p) {
     double v;
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -218,12 +228,20 @@ __device__ __forceinline__ float ld_spec(const float *p) {
 // in-place modes read and write the same array in one launch: no read-only (.nc) path there
 __device__ __forceinline__ double ld_spec_rw(const double *p) {
     double v;
+#if LBM_SPEC_LD == 1
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#else
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ float ld_spec_rw(const float *p) {
     float v;
+#if LBM_SPEC_LD == 1
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#else
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+#endif
     return v;
 }
 
@@ -360,32 +378,54 @@ __device__ __forceinline__ void finish_cell(const StepParams<T> &p, long long c,
     }
 }
 
+// Programmatic dependent launch: a step kernel lets the next launch of the stream start as soon as all of its
+// own CTAs are resident (grid_dep_launch, first instruction), and waits for the previous launch to be complete
+// and visible only where it first touches populations (grid_dep_wait) -- geometry words, records and link
+// lists are never written by a step, so their loads and the launch latency itself (2 - 3 us, a third of a
+// 64^3 step) overlap the previous step's tail.  Both are no-ops when the launch does not carry the attribute.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Used by the in-place storages only: the two-buffer kernels read through the non-coherent path (ld.global.nc),
+// whose contract -- read-only for the lifetime of the kernel -- an early-started kernel would break.
+
 template <typename T, bool STRICT, bool MOMENTS, bool RESID, bool SPEC, int CFG, int MODE>
 __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(const __grid_constant__ StepParams<T> p) {
     const Box &b = p.box;
     // 64-bit cell ids on purpose: 32-bit ones turn every address into one IMAD.WIDE.U32 instead of an
     // IADD3 pair (-22 instructions per thread), which changes nothing in fp64 and costs 6 % in fp32,
     // where IMAD shares its pipe with the collision's FFMAs (profiles/r01_notes.md)
+    if (MODE != MODE_AB) grid_dep_launch();
     const long long c = p.c_begin + (long long)blockIdx.x * cfg_block(CFG) + threadIdx.x;
     if (c >= p.c_end) return;  // ranges are whole planes (multiples of 32 cells): warp-uniform
     T f[Q];
     uint32_t node, wallw = 0u;
     const uint32_t kind = p.seg[c >> 5];
     if (SPEC) {
-        // every thread pulls; the buffers carry guards so all addresses are mapped
-        node = p.node[c];
+        // every thread pulls before it knows what its cell is; the buffers carry guards so all addresses are
+        // mapped.  The node / wall words are fetched afterwards and for mixed segments only (in a box that is
+        // mostly bulk they were 4 of the 156 bytes a fp32 cell moves), while the populations are in flight.
+#ifdef LBM_SELFCHECK
+        node = p.node[c];  // the checked build wants to know which reads are dropped
+#endif
+        if (MODE != MODE_AB) grid_dep_wait();
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             // every thread pulls, a non-fluid one drops what it read: bounds always, ownership only when used
+#ifdef LBM_SELFCHECK
             if (node & NODE_SKIP) LBM_CHK_BOUNDS(p, p.pull_base[q] + c);
             else LBM_CHK(p, p.pull_base[q] + c);
+#endif
             f[q] = MODE == MODE_AB ? ld_spec(p.pull_base[q] + c) : ld_spec_rw(p.pull_base[q] + c);
         }
         if (kind == SEG_EMPTY) return;
+        node = kind == SEG_MIXED ? p.node[c] : 0u;
+        wallw = kind == SEG_MIXED ? p.wall[c] : 0u;
     } else {
         if (kind == SEG_EMPTY) return;
         node = kind == SEG_MIXED ? p.node[c] : 0u;
         wallw = kind == SEG_MIXED ? p.wall[c] : 0u;
+        if (MODE != MODE_AB) grid_dep_wait();
     }
     double velsum = 0.0;
     if (!(node & NODE_SKIP)) {
@@ -396,7 +436,7 @@ __global__ void __launch_bounds__(cfg_block(CFG), cfg_minb(CFG)) k_step_dense(co
                 f[q] = MODE == MODE_AB ? ld_stream(p.pull_base[q] + c) : p.pull_base[q][c];
             }
         }
-        finish_cell<T, STRICT, MOMENTS, RESID, MODE, !SPEC>(p, c, node, wallw, f, velsum);
+        finish_cell<T, STRICT, MOMENTS, RESID, MODE, true>(p, c, node, wallw, f, velsum);
     }
     if (RESID) {
         // warp shuffle tree, then one atomic per warp
@@ -410,9 +450,14 @@ template <typename T, bool STRICT, bool MOMENTS, bool RESID, int CFG, int MODE>
 cudaError_t launch_mode(const StepParams<T> &p, cudaStream_t s) {
     constexpr int B = cfg_block(CFG);
     const unsigned nb = (unsigned)((p.c_end - p.c_begin + B - 1) / B);
-    if (p.speculative) k_step_dense<T, STRICT, MOMENTS, RESID, true, CFG, MODE><<<nb, B, 0, s>>>(p);
-    else k_step_dense<T, STRICT, MOMENTS, RESID, false, CFG, MODE><<<nb, B, 0, s>>>(p);
-    return cudaGetLastError();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nb), cfg.blockDim = dim3(B), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+    cfg.attrs = at, cfg.numAttrs = (MODE != MODE_AB && p.pdl) ? 1 : 0;
+    if (p.speculative) return cudaLaunchKernelEx(&cfg, k_step_dense<T, STRICT, MOMENTS, RESID, true, CFG, MODE>, p);
+    return cudaLaunchKernelEx(&cfg, k_step_dense<T, STRICT, MOMENTS, RESID, false, CFG, MODE>, p);
 }
 
 template <typename T, bool STRICT, bool MOMENTS, bool RESID>

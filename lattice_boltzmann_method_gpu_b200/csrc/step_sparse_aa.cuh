@@ -94,14 +94,6 @@ __device__ __forceinline__ void own_slot_bc(const SparseParams<T> &sp, long long
     }
 }
 
-// Programmatic dependent launch: a step kernel lets the next launch of the stream start as soon as all of its
-// own CTAs are resident (grid_dep_launch, first instruction), and waits for the previous launch to be complete
-// and visible only where it first touches populations (grid_dep_wait) -- geometry words, records and link
-// lists are never written by a step, so their loads and the launch latency itself (2 - 3 us, a third of a
-// 64^3 step) overlap the previous step's tail.  Both are no-ops when the launch does not carry the attribute.
-__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // per-step switches that are template parameters of the one-step kernels and run-time values of the
 // persistent one
 struct AaStep {

@@ -178,6 +178,87 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_aa_odd(T *__restrict__ f_, P p,
     for (int q = 0; q < Q; q++) f_[q * p.qs + c + (cxq(q) + (long long)p.px * cyq(q) + p.plane * czq(q))] = f[q];
 }
 
+// ---- two cells per thread, 64-bit (fp32) / 128-bit (fp64) accesses: half the memory requests per byte
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type mk2(T a, T b) { typename Vec2<T>::type v; v.x = a, v.y = b; return v; }
+
+template <typename T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_copy19_v2(const T *__restrict__ src, T *__restrict__ dst, P p) {
+    using V = typename Vec2<T>::type;
+    long long c = p.c0 + ((long long)blockIdx.x * BLOCK + threadIdx.x) * 2;
+    if (c >= p.c1) return;
+    V f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = *reinterpret_cast<const V *>(src + q * p.qs + c);
+#pragma unroll
+    for (int q = 0; q < Q; q++) *reinterpret_cast<V *>(dst + q * p.qs + c) = f[q];
+}
+template <typename T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_aa_even_v2(T *__restrict__ f_, P p, T inv_tau) {
+    using V = typename Vec2<T>::type;
+    long long c = p.c0 + ((long long)blockIdx.x * BLOCK + threadIdx.x) * 2;
+    if (c >= p.c1) return;
+    constexpr int opp[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+    T f0[Q], f1[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        V v = *reinterpret_cast<const V *>(f_ + q * p.qs + c);
+        f0[q] = v.x, f1[q] = v.y;
+    }
+    collide<T>(f0, inv_tau);
+    collide<T>(f1, inv_tau);
+#pragma unroll
+    for (int q = 0; q < Q; q++) *reinterpret_cast<V *>(f_ + opp[q] * p.qs + c) = mk2<T>(f0[q], f1[q]);
+}
+template <typename T, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_aa_odd_v2(T *__restrict__ f_, P p, T inv_tau) {
+    using V = typename Vec2<T>::type;
+    long long c = p.c0 + ((long long)blockIdx.x * BLOCK + threadIdx.x) * 2;
+    if (c >= p.c1) return;  // whole warps only (n is a multiple of 64 here)
+    const int lane = threadIdx.x & 31;
+    constexpr int opp[Q] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15};
+    T f0[Q], f1[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const long long off = (long long)p.px * cyq(q) + p.plane * czq(q);
+        const T *row = f_ + opp[q] * p.qs + c - off;  // this thread's aligned pair in the source row
+        V v = *reinterpret_cast<const V *>(row);
+        if (cxq(q) == 0) {
+            f0[q] = v.x, f1[q] = v.y;
+        } else if (cxq(q) == 1) {  // cells c, c+1 pull from c-1, c
+            T up = __shfl_up_sync(0xffffffffu, v.y, 1);
+            if (lane == 0) up = row[-1];
+            f0[q] = up, f1[q] = v.x;
+        } else {  // from c+1, c+2
+            T dn = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) dn = row[2];
+            f0[q] = v.y, f1[q] = dn;
+        }
+    }
+    collide<T>(f0, inv_tau);
+    collide<T>(f1, inv_tau);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const long long off = (long long)p.px * cyq(q) + p.plane * czq(q);
+        T *row = f_ + q * p.qs + c + off;  // aligned pair in the target row
+        if (cxq(q) == 0) {
+            *reinterpret_cast<V *>(row) = mk2<T>(f0[q], f1[q]);
+        } else if (cxq(q) == 1) {  // values go to c+1, c+2: the aligned pair (c, c+1) gets (left neighbour's f1, own f0)
+            const T left = __shfl_up_sync(0xffffffffu, f1[q], 1);
+            if (lane == 0) row[1] = f0[q];
+            else *reinterpret_cast<V *>(row) = mk2<T>(left, f0[q]);
+            if (lane == 31) row[2] = f1[q];
+        } else {  // values go to c-1, c: the aligned pair (c, c+1) gets (own f1, right neighbour's f0)
+            const T right = __shfl_down_sync(0xffffffffu, f0[q], 1);
+            if (lane == 31) row[0] = f1[q];
+            else *reinterpret_cast<V *>(row) = mk2<T>(f1[q], right);
+            if (lane == 0) row[-1] = f0[q];
+        }
+    }
+}
+
 template <typename F>
 float time_it(F launch, int reps = 10) {
     cudaEvent_t e0, e1;
@@ -203,6 +284,7 @@ __global__ void k_fill(T *f, long long n, long long qs) {
     for (int q = 0; q < Q; q++) f[q * qs + i] = (T)(w[q] * (1.0 + 1e-3 * ((i * 7 + q) % 13)));
 }
 
+static int g_only = 0;  // 1: only the AA 1-cell/thread b128 minb6 pair (for ncu)
 template <typename T>
 void run(int N, long long qpad) {
     const int px = ((N + 31) / 32) * 32;
@@ -223,6 +305,10 @@ void run(int N, long long qpad) {
     auto rep = [&](const char *name, float ms) { printf("%-44s %8.3f ms  %8.1f GB/s  %8.1f MLUPS\n", name, ms, gb / (ms * 1e-3), n / (ms * 1e-3) / 1e6); fflush(stdout); };
     printf("N=%d %s  qstride pad=%lld elements  cells/launch=%lld  (%.2f GB algorithmic)\n", N, sizeof(T) == 8 ? "fp64" : "fp32", qpad, n, gb);
     unsigned g256 = (unsigned)((n + 255) / 256), g128 = (unsigned)((n + 127) / 128), g512 = (unsigned)((n + 511) / 512);
+    if (g_only == 1) {
+        rep("AA even+odd 1 cell/thread b128 minb6", time_it([&](int i) { if (i & 1) k_aa_odd<T, 128, 6><<<g128, 128>>>(a, p, it); else k_aa_even<T, 128, 6><<<g128, 128>>>(a, p, it); }));
+        return;
+    }
     {
         long long n2 = (long long)(sizeof(T) * p.qs * Q / sizeof(double2));
         float ms = time_it([&](int) { k_copy1<<<(unsigned)((n2 + 255) / 256), 256>>>((const double2 *)a, (double2 *)b, n2); });
@@ -259,6 +345,25 @@ void run(int N, long long qpad) {
     rep("AA even (local rd/wr, in place)", time_it([&](int) { k_aa_even<T, 256, 2><<<g256, 256>>>(a, p, it); }));
     rep("AA odd (shifted rd + shifted wr, in place)", time_it([&](int) { k_aa_odd<T, 256, 2><<<g256, 256>>>(a, p, it); }));
     rep("AA even+odd average", time_it([&](int i) { if (i & 1) k_aa_odd<T, 256, 2><<<g256, 256>>>(a, p, it); else k_aa_even<T, 256, 2><<<g256, 256>>>(a, p, it); }));
+    {
+        unsigned h128 = (unsigned)((n / 2 + 127) / 128), h256 = (unsigned)((n / 2 + 255) / 256);
+        rep("copy19, 2 cells/thread vector accesses", time_it([&](int i) { if (i & 1) k_copy19_v2<T, 256, 2><<<h256, 256>>>(b, a, p); else k_copy19_v2<T, 256, 2><<<h256, 256>>>(a, b, p); }));
+#define AA2(NAME, BLOCK, MINB, GRID)                                                                                          \
+    rep("AA even 2 cells/thread " NAME, time_it([&](int) { k_aa_even_v2<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); }));      \
+    rep("AA odd  2 cells/thread " NAME, time_it([&](int) { k_aa_odd_v2<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); }));       \
+    rep("AA even+odd 2 cells/thread " NAME, time_it([&](int i) { if (i & 1) k_aa_odd_v2<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); else k_aa_even_v2<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); }));
+        AA2("b128 minb3", 128, 3, h128)
+        AA2("b128 minb4", 128, 4, h128)
+        AA2("b128 minb5", 128, 5, h128)
+        AA2("b128 minb6", 128, 6, h128)
+        AA2("b256 minb2", 256, 2, h256)
+        AA2("b256 minb3", 256, 3, h256)
+#define AA1(NAME, BLOCK, MINB, GRID) rep("AA even+odd 1 cell/thread " NAME, time_it([&](int i) { if (i & 1) k_aa_odd<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); else k_aa_even<T, BLOCK, MINB><<<GRID, BLOCK>>>(a, p, it); }));
+        AA1("b128 minb6", 128, 6, g128)
+        AA1("b128 minb8", 128, 8, g128)
+        AA1("b128 minb10", 128, 10, g128)
+        AA1("b128 minb12", 128, 12, g128)
+    }
     CK(cudaFree(a));
     CK(cudaFree(b));
 }
@@ -267,6 +372,7 @@ int main(int argc, char **argv) {
     int N = argc > 1 ? atoi(argv[1]) : 512;
     int fp64 = argc > 2 ? atoi(argv[2]) : 1;
     long long qpad = argc > 3 ? atoll(argv[3]) : 64;
+    g_only = argc > 4 ? atoi(argv[4]) : 0;
     if (fp64) run<double>(N, qpad);
     else run<float>(N, qpad);
     return 0;
