@@ -467,26 +467,37 @@ def run_ours(args):
         pinned = [torch.empty(nstored, dtype=torch.float64 if args.precision == "f64" else torch.float32).pin_memory()
                   for _ in range(4)]
         outs = [p.numpy() for p in pinned]
-        barrier()
-        t0 = time.perf_counter()
-        c = setup(build_case())
-        t1 = time.perf_counter()
-        c.step(args.steps)
-        t2 = time.perf_counter()
-        c.get_fields(outs)
-        barrier()
-        t_e2e = time.perf_counter() - t0
-        phases = {"setup_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": time.perf_counter() - t2, "cores_bound_near_gpu": numa}
-        if getattr(c, "timing", None):
-            phases["setup_breakdown_s"] = {k: round(v, 4) for k, v in c.timing.items()}
-        if world > 1:
-            t_ = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            t_e2e = float(t_.item())
+        # the whole job e2e_reps times, the median reported: cudaMalloc of the 27 GB slab alone varies between 10 ms
+        # and several 100 ms from run to run on a shared host (tools/setup_probe.py), which is not the library's doing
+        runs = []
+        for rep in range(max(1, args.e2e_reps)):
+            if rep:
+                c.close()
+                del c
+            barrier()
+            t0 = time.perf_counter()
+            c = setup(build_case())
+            t1 = time.perf_counter()
+            c.step(args.steps)
+            t2 = time.perf_counter()
+            c.get_fields(outs)
+            barrier()
+            t_run = time.perf_counter() - t0
+            ph = {"setup_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": time.perf_counter() - t2, "cores_bound_near_gpu": numa}
+            if getattr(c, "timing", None):
+                ph["setup_breakdown_s"] = {k: round(v, 4) for k, v in c.timing.items()}
+            if world > 1:
+                t_ = torch.tensor([t_run], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                t_run = float(t_.item())
+            runs.append((t_run, ph))
+        order = sorted(range(len(runs)), key=lambda i: runs[i][0])
+        t_e2e, phases = runs[order[len(order) // 2]]
+        phases["all_runs_s"] = [round(r[0], 4) for r in runs]
         e2e = {"value": nfluid * args.steps / t_e2e / 1e6, "unit": "MLUPS",
                "h2d_bytes_per_step": int(__import__("ctypes").sizeof(L.CaseDesc) / args.steps),
                "d2h_bytes_per_step": int(world * 4 * nstored * outs[0].itemsize / args.steps),
-               "what": f"create+geo_pre+index_transform+initialize, {args.steps} steps, D2H of rho,ux,uy,uz into pinned host buffers; "
+               "what": f"median of {len(runs)} runs of: create+geo_pre+index_transform+initialize, {args.steps} steps, D2H of rho,ux,uy,uz into pinned host buffers; "
                        "the case is described by a 4.7 KB descriptor (the LDC mask is analytic, ldc.cu:468-502), so H2D is only that",
                "seconds": t_e2e, "phases": phases}
         assert float(np.abs(outs[3]).max()) > 0.0
@@ -540,6 +551,7 @@ def main():
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: peer stores fused into the step kernel, or pack + NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-reps", type=int, default=3, help="end-to-end runs; the median is reported")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity_check")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128)
