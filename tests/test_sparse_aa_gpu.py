@@ -238,3 +238,31 @@ def test_persistent_convergence_loop_stops_on_the_same_iteration():
     if res[0][0][0] == res[1][0][0]:
         for x, y in zip(res[0][1], res[1][1]):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("storage_name", ["sparse_aa", "dense_aa"])
+@pytest.mark.parametrize("name,n", [("ldc", 40), ("bif", None), ("pos", 32)])
+def test_overlapped_launches_equal_serialised_launches(storage_name, name, n):
+    """in-place storages launch their step kernels with programmatic stream serialization (the next kernel starts
+    while the previous one drains and waits at griddepcontrol.wait before its first population load,
+    csrc/step_dense.cuh grid_dep_launch / grid_dep_wait): same bits as ordinary launches and as the oracle, FAST
+    arithmetic against itself, STRICT against the oracle; many short launches in a row so that several are in flight"""
+    L = S()
+    storage = L.STORE_SPARSE_AA if storage_name == "sparse_aa" else L.STORE_DENSE_AA
+    for math, prec, dt in ((L.MATH_FAST, L.F32, np.float32), (L.MATH_STRICT, L.F64, np.float64)):
+        runs = []
+        for overlap in (1, 0):
+            c = H.gpu_case(name, n, prec, math, storage=storage)
+            H.gpu_setup(c, name)
+            c.set_option("overlap_launches", overlap)
+            for nsteps in (1, 2, 50, 151):
+                c.step(nsteps)
+            runs.append([a.copy() for a in c.get_fields()])
+            c.close()
+        for x, y in zip(*runs):
+            assert np.array_equal(x, y)
+        if math == L.MATH_STRICT:
+            o, *_ = H.oracle_case(name, n, dt)
+            o.step(204)
+            for r, g in zip(o.fields(), runs[0]):
+                assert np.array_equal(r, g)
