@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "lbm_internal.h"
+#include "geo_text.h"
 #include "vtk_format.h"
 
 namespace lbm {
@@ -311,26 +312,24 @@ struct Solver final : SolverBase {
     }
 
     int load_flag_file() {
-        FILE *f = fopen(d.geo_path, "r");
-        if (!f) FAIL(LBM_ERR_IO, "cannot open geometry file '%s'", d.geo_path);
-        h_flag.assign((size_t)d.nx * d.ny * d.nz, 0);
-        long cnt = 0;
-        int tmp;
-        // bif.cu:50-61 (x fastest) or cor.cu:45-56 (y fastest)
-        for (int z = 0; z < d.nz; z++) {
-            const int n1 = d.geo_yfast ? d.nx : d.ny, n2 = d.geo_yfast ? d.ny : d.nx;
-            for (int a = 0; a < n1; a++)
-                for (int b = 0; b < n2; b++) {
-                    if (fscanf(f, "%d ", &tmp) != 1) tmp = 0;
-                    else cnt++;
-                    int x = d.geo_yfast ? a : b, y = d.geo_yfast ? b : a;
-                    h_flag[(size_t)x + (size_t)d.nx * ((size_t)y + (size_t)d.ny * z)] = tmp;
-                }
+        // bif.cu:50-61 (x fastest) or cor.cu:45-56 (y fastest); mapped and parsed by several threads (geo_text.h)
+        MappedFile f;
+        if (!f.open_ro(d.geo_path)) FAIL(LBM_ERR_IO, "cannot open geometry file '%s'", d.geo_path);
+        const long total = (long)d.nx * d.ny * d.nz;
+        h_flag.assign((size_t)total, 0);
+        int32_t *out = h_flag.data();
+        const long nx = d.nx, ny = d.ny, plane = nx * ny;
+        long cnt;
+        if (!d.geo_yfast) {
+            cnt = parse_int_tokens(f.p, f.n, total, 16, [out](long t, int v) { out[t] = v; });
+        } else {  // token t = (z * nx + x) * ny + y
+            cnt = parse_int_tokens(f.p, f.n, total, 16, [out, nx, ny, plane](long t, int v) {
+                const long z = t / plane, r = t - z * plane, x = r / ny, y = r - x * ny;
+                out[x + nx * (y + ny * z)] = v;
+            });
         }
-        fclose(f);
-        if (cnt != (long)d.nx * d.ny * d.nz)
-            FAIL(LBM_ERR_IO, "geometry file '%s' holds %ld tokens, expected %ld", d.geo_path, cnt,
-                 (long)d.nx * d.ny * d.nz);
+        if (cnt < total)
+            FAIL(LBM_ERR_IO, "geometry file '%s' holds %ld tokens, expected %ld", d.geo_path, cnt, total);
         have_flag = true;
         return 0;
     }

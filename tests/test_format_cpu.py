@@ -1,5 +1,6 @@
-"""CPU: the ASCII-VTK float formatter of the library (csrc/vtk_format.h, std::to_chars general/6) writes
-exactly the characters the reference's `ofs << value << ' '` writes (ldc.cu:603-607,
+"""CPU: the ASCII-VTK float formatter of the library (csrc/vtk_format.h: vtk_write, a %g routine of its own
+that hands rounding ties to std::to_chars general/6; all 2^32 float patterns against to_chars:
+profiles/r02_format_exhaustive.txt) writes exactly the characters the reference's `ofs << value << ' '` writes (ldc.cu:603-607,
 bifurcation.cu:1140-1150) -- checked by a small C++ program on pseudo-random bit patterns of float and
 double, values of the solver's magnitudes and the special values."""
 import subprocess
