@@ -252,6 +252,56 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
+def vessel_edge(n, world):
+    """cube edge of the vessel workload: --n on one GPU, the same number of nodes per GPU on N (1024 at N = 8)"""
+    return n if world == 1 else int(round(n * world ** (1.0 / 3.0) / 32.0)) * 32
+
+
+def vessel_inputs(n, z0, z1, k=4, rfrac=0.38):
+    """host-side synthetic inputs of BASELINE config 5 (same generator as tools/sparse_bench.py and
+    tools/vessel_scale.py): planes z0..z1 of a k x k bundle of sinusoidally bent tubes along y as a uint8 voxel
+    field [z][y][x], and the parabolic inlet speed plane [z][x] (outlet: pressure, zero plane)"""
+    sys.path.insert(0, str(ROOT / "tools"))
+    from sparse_bench import tube_bundle
+
+    flag = tube_bundle(n, k, rfrac, z0, z1).astype(np.uint8)
+    pitch = n / k
+    zz, xx = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    rr2 = ((xx % pitch - pitch / 2) ** 2 + (zz % pitch - pitch / 2) ** 2) / (rfrac * pitch) ** 2
+    inlet = (0.05 * np.clip(1 - rr2, 0, None)).astype(np.float32)
+    return flag, inlet
+
+
+def vessel_desc(L, n, z_range, prec, storage, math, device):
+    d = L.case_defaults(L.CASE_GEO_Y_INOUT)
+    d.nx = d.ny = d.nz = n
+    d.z_begin, d.z_end = z_range
+    d.precision, d.storage, d.math, d.device = prec, storage, math, device
+    d.pulse_amp, d.pulse_period = 0.3, 200.0  # pulsatile inlet (curved vessel/README.md:1: planned by the reference, never written)
+    d.bc[0].pulsatile = 1
+    return d
+
+
+def parity_check_vessel(args, L, prec, local, n, flag, inlet, steps):
+    """benchmarked storage (FAST) vs box-dense two-buffer STRICT on the benchmarked vessel, same step count"""
+    fields = {}
+    st = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA, "sparse": L.STORE_SPARSE_AB}[args.storage]
+    for name, storage, math in (("bench", st, L.MATH_FAST), ("strict_ab", L.STORE_DENSE_AB, L.MATH_STRICT)):
+        c = L.Case(vessel_desc(L, n, (0, n), prec, storage, math, local))
+        c.set_flag_slab(flag, 0)
+        c.geo_pre(), c.index_transform(), c.set_bc_planes(inlet, np.zeros_like(inlet)), c.initialize()
+        c.step(steps)
+        fields[name] = c.get_fields()
+        c.close()
+        del c
+    scale = max(float(np.abs(a).max()) for a in fields["strict_ab"][1:])
+    err = max(float(np.abs(a - b).max()) / (1.0 if k == 0 else scale) for k, (a, b) in enumerate(zip(fields["bench"], fields["strict_ab"])))
+    tol = 1e-10 if args.precision == "f64" else 2e-4
+    return {"what": f"vessel bundle {n}^3 {args.precision}, {steps} steps: bench storage '{args.storage}' FAST vs box-dense two-buffer "
+                    "STRICT (the arithmetic that is bit-exact with the CPU oracle in tests/); max over rho,ux,uy,uz relative to max|u|",
+            "max_rel_err": err, "tol": tol, "ok": bool(err <= tol)}
+
+
 def parity_check_single(args, L, prec, local, nfluid_expected):
     """benchmarked kernel (in-place, FAST) vs two-buffer STRICT on the benchmarked box, same step count"""
     n, steps = args.n, args.warmup + args.steps
@@ -350,6 +400,14 @@ def parity_check_multi(args, L, slab, prec, rank, world, local):
 
 def workload_config(args, world):
     n = args.n
+    if args.workload == "vessel":
+        e = vessel_edge(n, world)
+        return {"workload": f"vessel bundle {e}^3 (4x4 sinusoidally bent tubes along y, ~43 % of the box is fluid), D3Q19 BGK {args.precision}, "
+                            f"parabolic pulsatile velocity inlet (amplitude 0.3, period 200 steps), pressure outlet, bifurcation.cu rules; "
+                            f"z-slabs of {e // world} planes per GPU (BASELINE config 5)",
+                "storage": args.storage, "math": "fast", "bytes_per_node_update": BYTES_PER_LU[args.precision],
+                "parallelism": f"zslab{world}", "halo_exchange": args.halo if world > 1 else None,
+                "l2_policy": "working set (>=10 GB) far exceeds the 126 MB L2; no flush needed"}
     gx, gy, gz = global_dims(args, world)
     return {"workload": f"dense lid-driven cavity {gx}x{gy}x{gz} D3Q19 BGK {args.precision}, tau=0.55, Re~222 (ldc.cu rules), "
                         f"z-slabs of {gz // world} planes per GPU",
@@ -377,13 +435,21 @@ def run_ours(args):
     storage = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse_aa": L.STORE_SPARSE_AA, "sparse": L.STORE_SPARSE_AB}[args.storage]
     dtype = np.float64 if args.precision == "f64" else np.float32
 
-    gnx, gny, gnz = global_dims(args, world)
+    vessel = args.workload == "vessel"
+    gnx, gny, gnz = (vessel_edge(n, world),) * 3 if vessel else global_dims(args, world)
     z_lo, z_hi = slab.slab_ranges(gnz, world)[rank]
     parity = None
     if not args.no_parity and world > 1:
         parity = parity_check_multi(args, L, slab, prec, rank, world, local)
+    if vessel:  # the planes of the voxel field this rank reads (its slab +- 3), generated once, outside every timed region
+        fz0, fz1 = max(0, z_lo - 3), min(gnz, z_hi + 3)
+        v_flag, v_inlet = vessel_inputs(gnz, fz0, fz1)
+        v_zero = np.zeros_like(v_inlet)
 
     def build_case():
+        if vessel:
+            d = vessel_desc(L, gnz, (z_lo, z_hi), prec, storage, L.MATH_FAST, local)
+            return slab.SlabCase(d) if world > 1 else L.Case(d)
         d = L.case_defaults(L.CASE_LDC)
         d.nx, d.ny, d.nz = gnx, gny, gnz
         d.z_begin, d.z_end = z_lo, z_hi
@@ -394,20 +460,27 @@ def run_ours(args):
         """returns the case ready to step (a different one if the peer mapping is unavailable)"""
         nonlocal storage
         if world == 1:
+            if vessel:
+                c.set_flag_slab(v_flag, fz0)
             c.geo_pre()
             c.index_transform()
+            if vessel:
+                c.set_bc_planes(v_inlet, v_zero)
             c.initialize()
             return c
         if args.halo != "p2p" and storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
             raise SystemExit("in-place storages exchange slab faces by peer stores only: use --halo p2p or --storage ab")
-        c.setup()
+        if vessel:
+            c.setup(flag_slab=(v_flag, fz0), bc_planes=(v_inlet, v_zero))
+        else:
+            c.setup()
         if args.halo == "p2p" and not c.enable_p2p():  # the decision is all-reduced: every rank takes the same branch
             args.halo = "nccl (peer mapping unavailable)"
             if storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
                 c.close()
                 storage, args.storage = L.STORE_DENSE_AB, "ab"
                 c = build_case()
-                c.setup()
+                c.setup(flag_slab=(v_flag, fz0), bc_planes=(v_inlet, v_zero)) if vessel else c.setup()
         return c
 
     c = setup(build_case())
@@ -416,7 +489,8 @@ def run_ours(args):
     if not args.no_parity and world == 1 and not args.dims:
         c.close()
         del c
-        parity = parity_check_single(args, L, prec, local, nfluid_local)
+        parity = (parity_check_vessel(args, L, prec, local, gnz, v_flag, v_inlet, args.warmup + args.steps) if vessel
+                  else parity_check_single(args, L, prec, local, nfluid_local))
         c = setup(build_case())
     if world > 1:
         t_ = torch.tensor([nfluid_local], dtype=torch.int64, device="cuda")
@@ -460,10 +534,11 @@ def run_ours(args):
     # ---- end to end through the C ABI from host memory
     e2e = None
     if not args.no_e2e:
+        nstored_v = c.local_stored_count() if vessel else 0
         c.close()
         del c
         torch.cuda.empty_cache()
-        nstored = gnx * gny * (z_hi - z_lo)  # LDC stores every node of the slab
+        nstored = nstored_v if vessel else gnx * gny * (z_hi - z_lo)  # LDC stores every node of the slab
         pinned = [torch.empty(nstored, dtype=torch.float64 if args.precision == "f64" else torch.float32).pin_memory()
                   for _ in range(4)]
         outs = [p.numpy() for p in pinned]
@@ -495,12 +570,13 @@ def run_ours(args):
         t_e2e, phases = runs[order[len(order) // 2]]
         phases["all_runs_s"] = [round(r[0], 4) for r in runs]
         e2e = {"value": nfluid * args.steps / t_e2e / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(__import__("ctypes").sizeof(L.CaseDesc) / args.steps),
+               "h2d_bytes_per_step": int((__import__("ctypes").sizeof(L.CaseDesc) + (world * (v_flag.nbytes + 2 * v_inlet.nbytes) if vessel else 0)) / args.steps),
                "d2h_bytes_per_step": int(world * 4 * nstored * outs[0].itemsize / args.steps),
                "what": f"median of {len(runs)} runs of: create+geo_pre+index_transform+initialize, {args.steps} steps, D2H of rho,ux,uy,uz into pinned host buffers; "
-                       "the case is described by a 4.7 KB descriptor (the LDC mask is analytic, ldc.cu:468-502), so H2D is only that",
+                       + ("H2D: the descriptor, the uint8 voxel planes of the slab and the two boundary planes" if vessel else
+                          "the case is described by a 4.7 KB descriptor (the LDC mask is analytic, ldc.cu:468-502), so H2D is only that"),
                "seconds": t_e2e, "phases": phases}
-        assert float(np.abs(outs[3]).max()) > 0.0
+        assert max(float(np.abs(o).max()) for o in outs[1:]) > 0.0
 
     if rank == 0:
         cpu = None
@@ -509,14 +585,14 @@ def run_ours(args):
             v, t = cpu_oracle_mlups(cn, args.precision, csteps, 1)
             cpu = {"value": v, "unit": "MLUPS", "cores": 1, "kind": "port",
                    "sample": f"LDC {cn}^3 {args.precision}, {csteps} steps ({t:.1f} s) of the oracle's serial update+boundary_stream loop; "
-                             f"host has {os.cpu_count()} cores"}
+                             f"host has {os.cpu_count()} cores" + ("; the oracle's cost per fluid node does not depend on the geometry" if vessel else "")}
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS (fluid-node updates/s/1e6)", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(args.precision, n, args.storage),
+                         "traffic": args.traffic_bytes if args.traffic_bytes else ncu_traffic(args.precision, n, ("vessel_" if vessel else "") + args.storage),
                          "peak_source": peak_src,
                          "kernel": "k_step_dense" if args.storage in ("ab", "aa") else ("k_sparse_aa_even / k_sparse_aa_odd" if args.storage == "sparse_aa" else "k_step_sparse"), "algorithmic_bytes_per_launch": nfluid_local * bpl,
                          "frac_of_spec_8TBs": achieved / 8000.0},
@@ -543,13 +619,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--storage", default="aa", choices=["ab", "aa", "sparse_aa", "sparse"],
+    ap.add_argument("--storage", default=None, choices=["ab", "aa", "sparse_aa", "sparse"],
                     help="aa: box-dense, one population buffer streamed in place (default); ab: two buffers; "
                          "sparse_aa: fluid nodes only, one buffer, in place; sparse: reference compact order, two buffers")
     ap.add_argument("--dims", type=int, nargs=3, default=None, metavar=("NX", "NY", "NZ"),
                     help="global box (default n x n x n*gpus, i.e. weak scaling with one n^3 slab per GPU)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo exchange: peer stores fused into the step kernel, or pack + NCCL send/recv")
+    ap.add_argument("--workload", default="cavity", choices=["cavity", "vessel"],
+                    help="cavity: dense lid-driven cavity (BASELINE configs 2-3, the default); vessel: 4x4 bundle of bent tubes, "
+                         "~43 %% fluid, pulsatile inlet, sparse in-place storage (BASELINE config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-reps", type=int, default=3, help="end-to-end runs; the median is reported")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity_check")
@@ -560,6 +639,8 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram__bytes_read.sum+dram__bytes_write.sum per launch from the committed ncu capture")
     args = ap.parse_args()
+    if args.storage is None:
+        args.storage = "sparse_aa" if args.workload == "vessel" else "aa"
     args.warmup = max(args.warmup, 3)
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # started by hand without a launcher: become `torchrun --nproc-per-node N bench.py ...` (one rank per GPU)
