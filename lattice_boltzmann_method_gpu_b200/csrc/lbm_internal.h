@@ -253,6 +253,10 @@ template <typename T>
 cudaError_t launch_step_sparse_aa_fast(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
 template <typename T>
 cudaError_t launch_step_sparse_aa_strict(const SparseParams<T> &p, bool moments, bool resid, cudaStream_t s);
+template <typename T>
+cudaError_t preload_step_kernels_fast(int storage, bool speculative, bool peers, bool resid);
+template <typename T>
+cudaError_t preload_step_kernels_strict(int storage, bool speculative, bool peers, bool resid);
 // nsteps steps of a single-domain in-place sparse handle in ONE cooperative launch (grids that live in L2)
 template <typename T>
 cudaError_t launch_sparse_aa_persist_fast(const SparseParams<T> &p, int nsteps, int parity0, int moments_last, double *S,

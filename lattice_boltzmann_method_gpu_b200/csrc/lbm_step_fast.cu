@@ -41,3 +41,16 @@ template cudaError_t launch_sparse_aa_persist_fast<float>(const SparseParams<flo
 template cudaError_t launch_sparse_aa_persist_fast<double>(const SparseParams<double> &, int, int, int, double *, const double *,
                                                               unsigned *, int, cudaStream_t);
 }  // namespace lbm
+
+namespace lbm {
+// loads the step kernels a run loop of this storage is about to launch (step_dense.cuh preload_kernel);
+// resid: the variants that sum |u| (lbm_run_converge) or those that do not (lbm_run_fixed)
+template <typename T>
+cudaError_t preload_step_kernels_fast(int storage, bool speculative, bool peers, bool resid) {
+    if (storage == LBM_STORE_SPARSE_AA) return preload_step_sparse_aa_impl<T, false>(peers, resid);
+    if (storage == LBM_STORE_SPARSE_AB) return preload_step_sparse_impl<T, false>(resid);
+    return preload_step_dense_impl<T, false>(storage, speculative, resid);
+}
+template cudaError_t preload_step_kernels_fast<float>(int, bool, bool, bool);
+template cudaError_t preload_step_kernels_fast<double>(int, bool, bool, bool);
+}  // namespace lbm

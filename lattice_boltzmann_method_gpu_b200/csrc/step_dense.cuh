@@ -514,4 +514,38 @@ cudaError_t launch_step_dense_impl(const StepParams<T> &p_in, bool moments, bool
     return launch_cfg<T, STRICT, false, false>(p, storage, s);
 }
 
+// With lazy module loading (the CUDA default) a kernel is loaded the first time it is launched -- 5 to 10 ms
+// each for functions of this size, 18 ms of a 65 ms drivers/ldc run.  The run loops (lbm_run_fixed,
+// lbm_run_converge) ask for the attributes of the step kernels they are about to launch before they start their
+// clock, which loads them; lbm_step keeps the lazy behaviour (it would load variants it may never use).
+template <typename K>
+inline cudaError_t preload_kernel(K kernel) {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, kernel);
+}
+template <typename T, bool STRICT, bool SPEC, int MODE>
+cudaError_t preload_dense_mode(bool resid) {  // with and without moments
+    constexpr int C = default_cfg<T>();
+    cudaError_t e;
+    if (resid) {
+        if ((e = preload_kernel(k_step_dense<T, STRICT, false, true, SPEC, C, MODE>)) != cudaSuccess) return e;
+        return preload_kernel(k_step_dense<T, STRICT, true, true, SPEC, C, MODE>);
+    }
+    if ((e = preload_kernel(k_step_dense<T, STRICT, false, false, SPEC, C, MODE>)) != cudaSuccess) return e;
+    return preload_kernel(k_step_dense<T, STRICT, true, false, SPEC, C, MODE>);
+}
+template <typename T, bool STRICT>
+cudaError_t preload_step_dense_impl(int storage, bool speculative, bool resid) {
+    cudaError_t e;
+    if (storage == LBM_STORE_DENSE_AA) {
+        if (speculative) {
+            if ((e = preload_dense_mode<T, STRICT, true, MODE_AA_EVEN>(resid)) != cudaSuccess) return e;
+            return preload_dense_mode<T, STRICT, true, MODE_AA_ODD>(resid);
+        }
+        if ((e = preload_dense_mode<T, STRICT, false, MODE_AA_EVEN>(resid)) != cudaSuccess) return e;
+        return preload_dense_mode<T, STRICT, false, MODE_AA_ODD>(resid);
+    }
+    return speculative ? preload_dense_mode<T, STRICT, true, MODE_AB>(resid) : preload_dense_mode<T, STRICT, false, MODE_AB>(resid);
+}
+
 }  // namespace lbm

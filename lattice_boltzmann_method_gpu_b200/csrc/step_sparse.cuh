@@ -150,4 +150,15 @@ cudaError_t launch_step_sparse_impl(const SparseParams<T> &p_in, bool moments, b
     return cudaGetLastError();
 }
 
+template <typename T, bool STRICT>
+cudaError_t preload_step_sparse_impl(bool resid) {
+    cudaError_t e;
+    if (resid) {
+        if ((e = preload_kernel(k_step_sparse<T, STRICT, false, true>)) != cudaSuccess) return e;
+        return preload_kernel(k_step_sparse<T, STRICT, true, true>);
+    }
+    if ((e = preload_kernel(k_step_sparse<T, STRICT, false, false>)) != cudaSuccess) return e;
+    return preload_kernel(k_step_sparse<T, STRICT, true, false>);
+}
+
 }  // namespace lbm

@@ -387,4 +387,23 @@ cudaError_t launch_step_sparse_aa_impl(const SparseParams<T> &p_in, bool moments
 #undef LBM_SPAA
 }
 
+template <typename T, bool STRICT, bool PEERS>
+cudaError_t preload_sparse_aa_peers(bool resid) {
+    cudaError_t e;
+#define LBM_PL(M, R)                                                                                      \
+    if ((e = preload_kernel(k_sparse_aa_even<T, STRICT, M, R, PEERS>)) != cudaSuccess) return e;          \
+    if ((e = preload_kernel(k_sparse_aa_odd<T, STRICT, M, R, PEERS>)) != cudaSuccess) return e;
+    if (resid) {
+        LBM_PL(false, true) LBM_PL(true, true)
+    } else {
+        LBM_PL(false, false) LBM_PL(true, false)
+    }
+#undef LBM_PL
+    return cudaSuccess;
+}
+template <typename T, bool STRICT>
+cudaError_t preload_step_sparse_aa_impl(bool peers, bool resid) {
+    return peers ? preload_sparse_aa_peers<T, STRICT, true>(resid) : preload_sparse_aa_peers<T, STRICT, false>(resid);
+}
+
 }  // namespace lbm

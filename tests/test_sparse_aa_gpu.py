@@ -266,3 +266,36 @@ def test_overlapped_launches_equal_serialised_launches(storage_name, name, n):
             o.step(204)
             for r, g in zip(o.fields(), runs[0]):
                 assert np.array_equal(r, g)
+
+
+@pytest.mark.parametrize("name,n,tol,stag", [("ldc", 24, 1e-5, 20), ("pos", 24, 1e-5, 7)])
+def test_convergence_loop_leaves_the_state_of_its_last_iteration(name, n, tol, stag):
+    """run_converge launches its steps in batches sized so that the stopping rule (ldc.cu:653-685) can never be met
+    inside one; the state afterwards IS the one after exactly `its` steps, stepping goes on from it correctly, and the
+    in-place sparse storage stops where the two-buffer storage stops (S is an atomic sum in another order: +-2)"""
+    L = S()
+    out = {}
+    for storage in (L.STORE_SPARSE_AA, L.STORE_DENSE_AB):
+        c = H.gpu_case(name, n, L.F64, L.MATH_STRICT, storage=storage)
+        H.gpu_setup(c, name)
+        its, res = c.run_converge(4000, tol, stag, 500, False)
+        assert c.step_count == its
+        f_stop = [a.copy() for a in c.get_fields()]
+        c.step(5)
+        out[storage] = (its, res, f_stop, [a.copy() for a in c.get_fields()])
+        c.close()
+    (ia, ra, fa, fa5), (ib, rb, fb, fb5) = out[L.STORE_SPARSE_AA], out[L.STORE_DENSE_AB]
+    assert 60 < ia < 4000 and abs(ia - ib) <= 2
+    c = H.gpu_case(name, n, L.F64, L.MATH_STRICT, storage=L.STORE_SPARSE_AA)
+    H.gpu_setup(c, name)
+    c.step(ia)
+    for x, y in zip(c.get_fields(), fa):
+        assert np.array_equal(x, y)
+    c.step(5)
+    for x, y in zip(c.get_fields(), fa5):
+        assert np.array_equal(x, y)
+    c.close()
+    if ia == ib:
+        assert ra == rb
+        for x, y in zip(fa, fb):
+            assert np.array_equal(x, y)

@@ -22,6 +22,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--calls", type=int, default=3)
     ap.add_argument("--overlap", type=int, default=-1, help="lbm_set_option('overlap_launches'): 0 / 1")
+    ap.add_argument("--converge", type=int, default=0, help="also time run_converge over this many iterations (no files, never stops early)")
+    ap.add_argument("--stag", type=int, default=50)
+    ap.add_argument("--tol", type=float, default=0.0)
+    ap.add_argument("--no-warm", action="store_true")
     a = ap.parse_args()
     import helpers as H  # case builders only
 
@@ -32,11 +36,20 @@ def main():
         c.set_option("persistent", a.persistent)
     if a.overlap >= 0:
         c.set_option("overlap_launches", a.overlap)
-    c.step(a.steps)
-    for _ in range(a.calls):
+    if not a.no_warm:
+        c.step(a.steps)
+    for _ in range(0 if a.no_warm else a.calls):
         ms = c.step_timed(a.steps)
         print(f"{a.case} {a.precision} {a.storage} persistent={a.persistent} overlap={a.overlap}: {ms / a.steps * 1e3:.2f} us/step, "
               f"{c.num_fluid * a.steps / (ms * 1e-3) / 1e6:.0f} MLUPS", flush=True)
+    if a.converge:
+        import time
+
+        for _ in range(2):
+            t0 = time.perf_counter()
+            its, res = c.run_converge(a.converge - 1, a.tol, a.stag, 10 ** 9, False)
+            dt = time.perf_counter() - t0
+            print(f"  run_converge stag_max={a.stag} tol={a.tol}: {its} iterations, {dt / its * 1e6:.2f} us/iteration", flush=True)
 
 
 if __name__ == "__main__":
