@@ -125,7 +125,8 @@ struct Solver final : SolverBase {
     int step_flags = 0;
     // host
     std::vector<int32_t> h_flag;  // global Cartesian, optional
-    std::vector<uint8_t> h_flag_slab;  // planes [slab_z0, slab_z0 + slab_nz) only, optional
+    std::vector<uint8_t> h_flag_slab;  // (unused since lbm_set_flag_slab uploads at once)
+    bool flag_on_device = false;       // d_flag holds the planes lbm_set_flag_slab was given
     int slab_z0 = 0, slab_nz = 0;
     std::vector<float> h_in, h_out;
     // device
@@ -295,6 +296,7 @@ struct Solver final : SolverBase {
         if (!flag) FAIL(LBM_ERR_ARG, "null flag");
         h_flag.assign(flag, flag + (size_t)d.nx * d.ny * d.nz);
         h_flag_slab.clear();
+        flag_on_device = false;
         have_flag = true;
         return 0;
     }
@@ -304,9 +306,16 @@ struct Solver final : SolverBase {
         if (z_first > ext.z0 || z_first + z_count < ext.z1)
             FAIL(LBM_ERR_ARG, "flag slab [%d,%d) does not cover the planes [%d,%d) this handle needs", z_first,
                  z_first + z_count, ext.z0, ext.z1);
-        h_flag_slab.assign(flag, flag + (size_t)d.nx * d.ny * z_count);
-        slab_z0 = z_first, slab_nz = z_count;
-        h_flag.clear();
+        // the planes this handle reads go straight into the padded device rows: no host copy is kept (a copy of a
+        // 512^3 field alone took 59 ms, more than geo_pre + index_transform + initialize together)
+        CK(cudaSetDevice(d.device));
+        if (!d_flag && dalloc(&d_flag, (size_t)ext.cells())) return LBM_ERR_NOMEM;
+        CK(cudaMemsetAsync(d_flag, 0, (size_t)ext.cells(), st));
+        CK(cudaMemcpy2DAsync(d_flag, (size_t)ext.px, flag + (size_t)d.nx * (size_t)d.ny * (size_t)(ext.z0 - z_first), (size_t)d.nx,
+                             (size_t)d.nx, (size_t)d.ny * (size_t)(ext.z1 - ext.z0), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        h_flag_slab.clear(), h_flag.clear();
+        flag_on_device = true;
         have_flag = true;
         return 0;
     }
@@ -343,19 +352,25 @@ struct Solver final : SolverBase {
         }
         if (!d_flag && dalloc(&d_flag, (size_t)ext.cells())) return LBM_ERR_NOMEM;
         if (!d_label_ext && dalloc(&d_label_ext, (size_t)ext.cells())) return LBM_ERR_NOMEM;
-        if (needs_file) {
-            // ext slab of the binary field, padded pitch, one byte per voxel
+        if (needs_file && flag_on_device) {
+            // lbm_set_flag_slab already put the planes there
+        } else if (needs_file) {
+            // ext slab of the global int32 field (geo.txt / lbm_set_flag), padded pitch, one byte per voxel
             std::vector<uint8_t> tmp((size_t)ext.cells(), 0);
-            for (int z = ext.z0; z < ext.z1; z++)
-                for (int y = 0; y < d.ny; y++) {
-                    uint8_t *drow = &tmp[(size_t)ext.px * ((size_t)y + (size_t)d.ny * (z - ext.z0))];
-                    if (!h_flag_slab.empty()) {
-                        memcpy(drow, &h_flag_slab[(size_t)d.nx * ((size_t)y + (size_t)d.ny * (z - slab_z0))], (size_t)d.nx);
-                    } else {
+            const int nthr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, ext.z1 - ext.z0}));
+            auto work = [&](int t) {
+                const int za = ext.z0 + (int)((long long)(ext.z1 - ext.z0) * t / nthr), zb = ext.z0 + (int)((long long)(ext.z1 - ext.z0) * (t + 1) / nthr);
+                for (int z = za; z < zb; z++)
+                    for (int y = 0; y < d.ny; y++) {
+                        uint8_t *drow = &tmp[(size_t)ext.px * ((size_t)y + (size_t)d.ny * (z - ext.z0))];
                         const int32_t *srow = &h_flag[(size_t)d.nx * ((size_t)y + (size_t)d.ny * z)];
                         for (int x = 0; x < d.nx; x++) drow[x] = (uint8_t)srow[x];
                     }
-                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nthr; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
             CK(cudaMemcpyAsync(d_flag, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, st));
             CK(cudaStreamSynchronize(st));
         } else if (d.case_rule == LBM_CASE_POISEUILLE) {

@@ -21,21 +21,36 @@ def main():
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--overlap", type=int, default=-1)
     ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--workload", default="cavity", choices=["cavity", "vessel"])
     a = ap.parse_args()
     st = {"ab": L.STORE_DENSE_AB, "aa": L.STORE_DENSE_AA, "sparse": L.STORE_SPARSE_AB, "sparse_aa": L.STORE_SPARSE_AA}[a.storage]
     torch.cuda.set_device(0)
+    prec = L.F64 if a.precision == "f64" else L.F32
+    if a.workload == "vessel":
+        import bench
+
+        flag, inlet = bench.vessel_inputs(a.n, 0, a.n)
     for r in range(a.rounds):
-        d = L.case_defaults(L.CASE_LDC)
-        d.nx = d.ny = d.nz = a.n
-        d.z_begin, d.z_end = 0, a.n
-        d.precision, d.storage, d.math, d.device = (L.F64 if a.precision == "f64" else L.F32), st, L.MATH_FAST, 0
+        if a.workload == "vessel":
+            d = bench.vessel_desc(L, a.n, (0, a.n), prec, st, L.MATH_FAST, 0)
+        else:
+            d = L.case_defaults(L.CASE_LDC)
+            d.nx = d.ny = d.nz = a.n
+            d.z_begin, d.z_end = 0, a.n
+            d.precision, d.storage, d.math, d.device = prec, st, L.MATH_FAST, 0
         t = [time.perf_counter()]
         c = L.Case(d)
         if a.overlap >= 0:
             c.set_option("overlap_launches", a.overlap)
+        if a.workload == "vessel":
+            t0 = time.perf_counter()
+            c.set_flag_slab(flag, 0)
+            print(f"  set_flag_slab {1e3 * (time.perf_counter() - t0):.1f} ms (inside 'create' below)")
         t.append(time.perf_counter())
         c.geo_pre(); torch.cuda.synchronize(); t.append(time.perf_counter())
         c.index_transform(); torch.cuda.synchronize(); t.append(time.perf_counter())
+        if a.workload == "vessel":
+            c.set_bc_planes(inlet, inlet * 0)
         c.initialize(); torch.cuda.synchronize(); t.append(time.perf_counter())
         c.step(1); t.append(time.perf_counter())
         c.step(20); t.append(time.perf_counter())
