@@ -79,19 +79,26 @@ def main():
         print("no /root/reference here: keeping prebuilt baseline/_ref/variants (if any)")
         return
     OUT.mkdir(parents=True, exist_ok=True)
-    for name, (src, edit, tex) in VARIANTS.items():
-        text = edit(src.read_text(errors="replace"))
-        cu = OUT / f"{name}.cu"
-        cu.write_text(text)
-        cmd = ["nvcc", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", f"-I{SHIM}", "-w"]
-        if tex:
-            cmd += ["-include", "texref_shim.h"]
-        cmd += ["-o", str(OUT / name), str(cu)]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode:
-            sys.stderr.write(r.stderr[-3000:])
-            raise SystemExit(f"nvcc failed for {name}")
-        print("built", OUT / name)
+    import tempfile
+
+    # the patched texts exist only in a temporary directory while nvcc runs: nothing but binaries is left in the
+    # repository tree (no copy of reference source, edited or not)
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (src, edit, tex) in VARIANTS.items():
+            text = edit(src.read_text(errors="replace"))
+            cu = Path(tmp) / f"{name}.cu"
+            cu.write_text(text)
+            cmd = ["nvcc", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", f"-I{SHIM}", "-w"]
+            if tex:
+                cmd += ["-include", "texref_shim.h"]
+            cmd += ["-o", str(OUT / name), str(cu)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode:
+                sys.stderr.write(r.stderr[-3000:])
+                raise SystemExit(f"nvcc failed for {name}")
+            print("built", OUT / name)
+    for stale in OUT.glob("*.cu"):
+        stale.unlink()
 
 
 if __name__ == "__main__":
