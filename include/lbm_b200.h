@@ -155,7 +155,8 @@ const char *lbm_last_error(lbm_handle h); /* h may be NULL: last create() error 
 int lbm_set_flag(lbm_handle h, const int32_t *flag_cartesian);
 /* Same for one z-slab of a large box: `flag` holds planes [z_first, z_first+z_count) only, one byte
  * per voxel, [z][y][x].  The planes must cover this handle's owned range extended by 3 planes on
- * each interior side (labels look 1 plane, the -1 marking 1 more, the halo 1 more). */
+ * each interior side (labels look 1 plane, the -1 marking 1 more, the halo 1 more).  The planes are
+ * uploaded to the device before the call returns; the caller's buffer is not referenced afterwards. */
 int lbm_set_flag_slab(lbm_handle h, const uint8_t *flag, int32_t z_first, int32_t z_count);
 
 /* geo_pre(): ldc:468-502, pos:52-254, bif:36-239, cor:31-260.  Reads geo_path
