@@ -360,6 +360,8 @@ def parity_check_multi(args, L, slab, prec, rank, world, local):
         c = slab.SlabCase(desc(z0, z1))
         c.setup(flag=flag, bc_planes=planes)
         fused = args.halo == "p2p" and c.enable_p2p()
+        if not fused and storage == L.STORE_DENSE_AA:
+            c.enable_staged()
         steps = 41
         c.step(steps)
         mine = [torch.from_numpy(a).cuda() for a in c.get_fields()]
@@ -468,15 +470,21 @@ def run_ours(args):
                 c.set_bc_planes(v_inlet, v_zero)
             c.initialize()
             return c
-        if args.halo != "p2p" and storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
-            raise SystemExit("in-place storages exchange slab faces by peer stores only: use --halo p2p or --storage ab")
+        if args.halo != "p2p" and storage == L.STORE_SPARSE_AA:
+            raise SystemExit("the sparse in-place storage exchanges slab faces by peer stores only: use --halo p2p or --storage aa / ab")
         if vessel:
             c.setup(flag_slab=(v_flag, fz0), bc_planes=(v_inlet, v_zero))
         else:
             c.setup()
+        if args.halo != "p2p" and storage == L.STORE_DENSE_AA:
+            c.enable_staged()  # mailbox exchange through staging buffers that NCCL send/recv moves
+            return c
         if args.halo == "p2p" and not c.enable_p2p():  # the decision is all-reduced: every rank takes the same branch
             args.halo = "nccl (peer mapping unavailable)"
-            if storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
+            if storage == L.STORE_DENSE_AA:
+                c.enable_staged()
+                return c
+            if storage == L.STORE_SPARSE_AA:
                 c.close()
                 storage, args.storage = L.STORE_DENSE_AB, "ab"
                 c = build_case()

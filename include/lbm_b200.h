@@ -315,6 +315,13 @@ int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync);
 int lbm_mail_export(lbm_handle h, int32_t side, lbm_ipc_handle *handle, void **ptr, int64_t *byte_offset, int64_t *stride,
                     int64_t *guard);
 int lbm_mail_attach(lbm_handle h, int32_t side, void *peer_mail);
+/* The same exchange where the neighbour's memory cannot be mapped (no peer access: the NCCL / copy transport).
+ * lbm_mail_stage(side) creates the mailbox of that side and two staging buffers; from then on the face launches
+ * store the leaving populations into the local send part, lbm_halo_buffers(side) returns the send / receive part
+ * of the current step (5 planes each), the caller moves send -> the neighbour's receive between lbm_step_begin and
+ * lbm_step_end (ordered on lbm_stream), and lbm_step_end merges what arrived into the mailbox.  Steps are driven
+ * with lbm_step_begin / lbm_step_interior / lbm_step_end as for the two-buffer storage. */
+int lbm_mail_stage(lbm_handle h, int32_t side);
 
 /* ---- several z-slabs driven from ONE process: the multi-GPU form of the reference's main() ----
  * (SURVEY 8b `lbm_create_distributed`; the reference is single-GPU, ldc.cu:612-717.)

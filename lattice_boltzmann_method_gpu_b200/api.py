@@ -79,7 +79,7 @@ ABI_SYMBOLS = [
     "lbm_device_bytes", "lbm_output_save", "lbm_set_output_format", "lbm_voxelize_stl", "lbm_voxelize_triangles", "lbm_voxel_last_error", "lbm_run_fixed", "lbm_run_converge", "lbm_halo_buffers",
     "lbm_step_begin", "lbm_step_interior", "lbm_step_end", "lbm_last_velsum", "lbm_stream", "lbm_sync",
     "lbm_p2p_export", "lbm_p2p_open", "lbm_p2p_close", "lbm_p2p_attach", "lbm_checkpoint_save", "lbm_checkpoint_load",
-    "lbm_slab_step", "lbm_sync_export", "lbm_sync_attach", "lbm_mail_export", "lbm_mail_attach", "lbm_write_bc_csv", "lbm_debug_selfcheck", "lbm_set_option",
+    "lbm_slab_step", "lbm_sync_export", "lbm_sync_attach", "lbm_mail_export", "lbm_mail_attach", "lbm_mail_stage", "lbm_write_bc_csv", "lbm_debug_selfcheck", "lbm_set_option",
     "lbm_create_distributed", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size", "lbm_group_slab",
     "lbm_group_setup", "lbm_group_step", "lbm_group_num_fluid", "lbm_group_residual", "lbm_group_get_fields",
     "lbm_group_get_index", "lbm_group_set_output_format", "lbm_group_output_save", "lbm_group_run_fixed",
@@ -157,6 +157,7 @@ def load_library() -> C.CDLL:
         "lbm_sync_attach": ([vp, i32, vp], C.c_int),
         "lbm_mail_export": ([vp, i32, vp, P(vp), P(i64), P(i64), P(i64)], C.c_int),
         "lbm_mail_attach": ([vp, i32, vp], C.c_int),
+        "lbm_mail_stage": ([vp, i32], C.c_int),
         "lbm_write_bc_csv": ([vp, C.c_char_p], C.c_int),
         "lbm_debug_selfcheck": ([vp, vp], C.c_int),
         "lbm_set_option": ([vp, C.c_char_p, dbl], C.c_int),
@@ -348,6 +349,10 @@ class Case:
 
     def mail_attach(self, side: int, peer_mail):
         self._ck(self._L.lbm_mail_attach(self._h, side, peer_mail))
+
+    def mail_stage(self, side: int):
+        """mailbox exchange of `side` through local staging buffers (transport without peer mapping)"""
+        self._ck(self._L.lbm_mail_stage(self._h, side))
 
     def sync_attach(self, side: int, peer_sync):
         self._ck(self._L.lbm_sync_attach(self._h, side, peer_sync))

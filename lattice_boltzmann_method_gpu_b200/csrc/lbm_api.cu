@@ -64,6 +64,7 @@ struct SolverBase {
     virtual int sync_attach(int side, void *peer_sync) = 0;
     virtual int mail_export(int side, lbm_ipc_handle *h, void **ptr, int64_t *boff, int64_t *ms, int64_t *guard) = 0;
     virtual int mail_attach(int side, void *peer_mail) = 0;
+    virtual int mail_stage(int side) = 0;
     virtual void set_inproc_neighbour(int side, SolverBase *nb) = 0;
     virtual cudaEvent_t face_event(int k) = 0;
     virtual int enqueue_step(int flags, double *acc_slot) = 0;  // begin + interior + end, no host sync
@@ -161,6 +162,8 @@ struct Solver final : SolverBase {
     T *d_mail[2] = {nullptr, nullptr}, *peer_mail[2] = {nullptr, nullptr};
     long long mail_ms = 0, mail_G = 0;
     bool mail_live[2] = {false, false};  // the mailbox, not the population buffer, holds the current values of its slots
+    T *d_stage_out[2] = {nullptr, nullptr}, *d_stage_in[2] = {nullptr, nullptr};  // staged mailboxes (lbm_mail_stage)
+    bool mail_staged[2] = {false, false};
     // neighbour ordering of slab steps: flags in peer memory (other process) or events (same process)
     unsigned long long *d_sync = nullptr;               // [0] low neighbour's progress, [1] high neighbour's, [2] timeout
     unsigned long long *peer_sync[2] = {nullptr, nullptr};  // where this slab reports its own progress, per side
@@ -199,7 +202,7 @@ struct Solver final : SolverBase {
         fr(d_send[0]), fr(d_send[1]), fr(d_recv[0]), fr(d_recv[1]), fr(d_acc), fr(d_cnt);
         fr(d_sid), fr(d_cmeta), fr(d_rec_links), fr(d_bcslot), fr(d_bclinks);
         fr(d_stage), fr(d_wall), fr(d_wallc), fr(d_cart), fr(d_chunk_off), fr(d_nodec), fr(d_labelc), fr(d_rec), fr(d_chunk_cnt), fr(d_plane_seg);
-        fr(d_mail[0]), fr(d_mail[1]);
+        fr(d_mail[0]), fr(d_mail[1]), fr(d_stage_out[0]), fr(d_stage_out[1]), fr(d_stage_in[0]), fr(d_stage_in[1]);
         fr(d_sync), fr(d_chk_shadow[0]), fr(d_chk_shadow[1]), fr(d_chk_count), fr(d_pulse), fr(d_barrier);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -577,6 +580,7 @@ struct Solver final : SolverBase {
         inproc_nb[0] = inproc_nb[1] = nullptr;
         peer_mail[0] = peer_mail[1] = nullptr;
         mail_live[0] = mail_live[1] = false;
+        mail_staged[0] = mail_staged[1] = false;
         sync_base = 0;
     }
 
@@ -996,6 +1000,15 @@ struct Solver final : SolverBase {
             else CK(launch_halo_unpack<T>(d_nxt, qstride, d_label8, fluid_label, box, box.z1 - box.z0 - 1, 1, d_recv[1], st));
             launches++;
         }
+        for (int sd = 0; sd < 2; sd++)
+            if ((sd == 0 ? lo_halo : hi_halo) && mail_staged[sd]) {
+                // take over what the neighbour stored (the transfer into the receive part is complete on this stream),
+                // and give the part that was sent its "nothing written" pattern back
+                const size_t off = (steps & 1) ? (size_t)mail_ms * 5 : 0;
+                CK(launch_mail_merge<T>(d_mail[sd] + off, d_stage_in[sd] + off, mail_ms * 5, st));
+                CK(cudaMemsetAsync(d_stage_out[sd] + off, 0xFF, (size_t)mail_ms * 5 * sizeof(T), st));
+                launches++;
+            }
         if ((step_flags & LBM_STEP_VELSUM) && !step_nosync) {
             CK(cudaMemcpyAsync(&last_S, d_acc, sizeof(double), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1142,7 +1155,24 @@ struct Solver final : SolverBase {
             mail_live[side] = false;
         }
         peer_mail[side] = (T *)pm;
+        mail_staged[side] = false;
         CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    // Mailbox transport WITHOUT peer mapping: the leaving populations of this side go into a local staging buffer
+    // (lbm_halo_buffers: send part), the caller moves it to the neighbour's receive part by whatever means it has
+    // (NCCL send/recv: slab.py; a device copy: tests) between lbm_step_begin and lbm_step_end, and lbm_step_end
+    // merges what arrived into the mailbox (k_mail_merge).  The step kernel is the one of the mapped transport.
+    int mail_stage(int side) override {
+        int r = mail_export(side, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (r) return r;
+        const size_t n = (size_t)mail_ms * 10;
+        if (!d_stage_out[side] && (dalloc(&d_stage_out[side], n) || dalloc(&d_stage_in[side], n))) return LBM_ERR_NOMEM;
+        CK(cudaMemsetAsync(d_stage_out[side], 0xFF, n * sizeof(T), st));
+        CK(cudaMemsetAsync(d_stage_in[side], 0xFF, n * sizeof(T), st));
+        r = mail_attach(side, d_stage_out[side]);
+        if (r) return r;
+        mail_staged[side] = true;
         return 0;
     }
     int sync_export(lbm_ipc_handle *h, void **ptr, int64_t *boff) override {
@@ -1362,6 +1392,14 @@ struct Solver final : SolverBase {
         if (side < 0 || side > 1) FAIL(LBM_ERR_ARG, "side must be 0 or 1");
         if (!have_init) FAIL(LBM_ERR_STATE, "halo_buffers before initialize");
         const bool present = side == 0 ? lo_halo : hi_halo;
+        if (present && mail_staged[side]) {  // the part of the current step's parity: A on even, B on odd steps
+            const size_t off = (steps & 1) ? (size_t)mail_ms * 5 : 0, bytes = (size_t)mail_ms * 5 * sizeof(T);
+            if (send) *send = d_stage_out[side] + off;
+            if (recv) *recv = d_stage_in[side] + off;
+            if (send_bytes) *send_bytes = bytes;
+            if (recv_bytes) *recv_bytes = bytes;
+            return 0;
+        }
         if (send) *send = present ? d_send[side] : nullptr;
         if (recv) *recv = present ? d_recv[side] : nullptr;
         const size_t dense_b = (size_t)box.plane * 5 * sizeof(T);
@@ -2245,6 +2283,7 @@ int lbm_mail_export(lbm_handle h, int32_t side, lbm_ipc_handle *handle, void **p
     return h->s->mail_export(side, handle, ptr, byte_offset, stride, guard);
 }
 int lbm_mail_attach(lbm_handle h, int32_t side, void *peer_mail) { H_OR_FAIL; return h->s->mail_attach(side, peer_mail); }
+int lbm_mail_stage(lbm_handle h, int32_t side) { H_OR_FAIL; return h->s->mail_stage(side); }
 int lbm_sync_attach(lbm_handle h, int32_t side, void *peer_sync) { H_OR_FAIL; return h->s->sync_attach(side, peer_sync); }
 int lbm_set_option(lbm_handle h, const char *name, double value) { H_OR_FAIL; return name ? h->s->set_option(name, value) : LBM_ERR_ARG; }
 int lbm_debug_selfcheck(lbm_handle h, uint64_t out[3]) { H_OR_FAIL; return out ? h->s->selfcheck(out) : LBM_ERR_ARG; }

@@ -1007,6 +1007,28 @@ cudaError_t launch_mail_copy(T *a, long long qstride, T *mail, long long ms, lon
 template cudaError_t launch_mail_copy<float>(float *, long long, float *, long long, long long, long long, long long, long long, int, int, cudaStream_t);
 template cudaError_t launch_mail_copy<double>(double *, long long, double *, long long, long long, long long, long long, long long, int, int, cudaStream_t);
 
+// Staged mailboxes (transport without peer mapping: NCCL send/recv or any other copy).  The step kernel stores the
+// leaving populations into a LOCAL staging buffer laid out like the neighbour's mailbox, prefilled with all-one
+// bits; after the transfer the receiver takes over exactly the elements the sender wrote -- the others belong to
+// the receiver's own boundary slots.  (All-one bits are a NaN no arithmetic produces.)
+template <typename T>
+__global__ void k_mail_merge(T *mail, const T *in, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T v = in[i];
+    bool written;
+    if (sizeof(T) == 8) written = __double_as_longlong((double)v) != -1LL;
+    else written = __float_as_int((float)v) != -1;
+    if (written) mail[i] = v;
+}
+template <typename T>
+cudaError_t launch_mail_merge(T *mail, const T *in, long long n, cudaStream_t s) {
+    k_mail_merge<T><<<nblocks(n, 256), 256, 0, s>>>(mail, in, n);
+    return cudaGetLastError();
+}
+template cudaError_t launch_mail_merge<float>(float *, const float *, long long, cudaStream_t);
+template cudaError_t launch_mail_merge<double>(double *, const double *, long long, cudaStream_t);
+
 // ---- neighbour handshake between z-slabs that live in different processes (one process per GPU)
 // A slab may start the face launches of step t+1 only after both neighbours finished the face launches of
 // step t (they read the halo plane this slab is about to overwrite, and wrote the one it is about to read).

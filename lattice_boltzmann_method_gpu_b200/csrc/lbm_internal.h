@@ -170,6 +170,8 @@ cudaError_t launch_halo_unpack(T *f, long long qstride, const int8_t *label8, in
 
 // mailbox <-> population buffer (dir 0: fill the mailbox from the buffer, 1: drain it back); see StepParams::mail
 template <typename T>
+cudaError_t launch_mail_merge(T *mail, const T *in, long long n, cudaStream_t s);
+template <typename T>
 cudaError_t launch_mail_copy(T *a, long long qstride, T *mail, long long ms, long long G, long long face_c0, long long halo_c0,
                              long long plane, int side, int dir, cudaStream_t s);
 // neighbour handshake of z-slabs in different processes (flags in peer memory), lbm_geo.cu

@@ -286,10 +286,28 @@ class SlabCase(api.Case):
                              torch.as_tensor(_DevBuf(r, max(nr, self.dtype.itemsize), self.dtype), device="cuda")[: nr // self.dtype.itemsize]))
         self._bufs = bufs
 
+    def enable_staged(self):
+        """In-place dense storage WITHOUT peer mapping (no peer access between the GPUs, or --halo nccl): the mailbox
+        exchange through local staging buffers that torch.distributed (NCCL send/recv) moves between the ranks
+        (lbm_mail_stage).  Steps are then driven like the two-buffer storage's: begin / exchange / interior / end."""
+        if self.desc.storage != api.STORE_DENSE_AA:
+            raise api.LbmError(-2, "staged mailboxes exist for the dense in-place storage only")
+        for side, present in ((0, self.rank > 0), (1, self.rank < self.world - 1)):
+            if present:
+                self.mail_stage(side)
+        self._staged, self._p2p = True, False
+        self._bufs_by_parity = {}
+
     def _one_step(self, flags=0):
         import torch
 
         self.step_begin(flags)  # face planes + pack, queued on the library's stream
+        if getattr(self, "_staged", False):  # the staging parts alternate with the step's parity (A / B)
+            par = self.step_count & 1
+            if par not in self._bufs_by_parity:
+                self._wrap_buffers()
+                self._bufs_by_parity[par] = self._bufs
+            self._bufs = self._bufs_by_parity[par]
         (s_lo, r_lo), (s_hi, r_hi) = self._bufs
         # torch.distributed orders NCCL's stream after what `self._ext` holds so far (faces + pack)
         with torch.cuda.stream(self._ext):

@@ -10,7 +10,7 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def run_slabs(name, n, P, steps, precision, math_mode, pulse=None, storage=None):
+def run_slabs(name, n, P, steps, precision, math_mode, pulse=None, storage=None, staged=False):
     import torch
 
     import lattice_boltzmann_method_gpu_b200 as L
@@ -28,6 +28,12 @@ def run_slabs(name, n, P, steps, precision, math_mode, pulse=None, storage=None)
         if name == "bif":
             c.set_bc_planes(*H.bif_bc_planes())
         c.initialize()
+    if staged:  # dense in-place storage, mailbox exchange through local staging buffers (lbm_mail_stage)
+        for r, c in enumerate(cs):
+            if r > 0:
+                c.mail_stage(0)
+            if r < P - 1:
+                c.mail_stage(1)
 
     def view(c, side):
         s, r, ns, nr = c.halo_buffers(side)
@@ -42,6 +48,8 @@ def run_slabs(name, n, P, steps, precision, math_mode, pulse=None, storage=None)
         flags = L.STEP_MOMENTS if it == steps - 1 else 0
         for c in cs:
             c.step_begin(flags)
+        if staged:  # the send / receive parts alternate with the step's parity
+            bufs = [(view(c, 0), view(c, 1)) for c in cs]
         for c in cs:
             c.step_interior()
             c.sync()
@@ -178,3 +186,58 @@ def test_fused_peer_store_halo_exchange(name, n, P, storage_name):
         assert np.array_equal(np.concatenate([c.get_fields()[k] for c in cs]), ref[k]), f"field {k}"
     # only step kernels ran: at most face(s) + interior per slab and step
     assert sum(c.launch_count for c in cs) - launches0 <= 3 * P * steps + 4 * P
+
+
+@pytest.mark.parametrize("name,n,P", [("ldc", 24, 3), ("ldc", 20, 5), ("pos", 24, 2), ("bif", None, 4), ("cor", None, 3)])
+@pytest.mark.parametrize("math_name,prec", [("strict", "f64"), ("fast", "f32")])
+def test_staged_mailboxes_equal_single_domain_bitwise(name, n, P, math_name, prec):
+    """the in-place dense storage over a transport WITHOUT peer mapping (lbm_mail_stage: the face launches store
+    into local staging buffers, a copy -- NCCL send/recv between processes, a device copy here -- moves them, and
+    lbm_step_end merges exactly the elements the neighbour wrote into the mailbox): P slabs == one domain, bit
+    for bit, both parities, every case rule"""
+    import lattice_boltzmann_method_gpu_b200 as L
+
+    mm = L.MATH_STRICT if math_name == "strict" else L.MATH_FAST
+    pr = L.F64 if prec == "f64" else L.F32
+    steps = 23
+    one = H.gpu_case(name, n, pr, mm, storage=L.STORE_DENSE_AA)
+    H.gpu_setup(one, name)
+    one.step(steps)
+    ref = one.get_fields()
+    cs, _ = run_slabs(name, n, P, steps, pr, mm, storage=L.STORE_DENSE_AA, staged=True)
+    for k in range(4):
+        got = np.concatenate([c.get_fields()[k] for c in cs])
+        assert np.array_equal(got, ref[k]), f"field {k}: max diff {np.abs(got - ref[k]).max()}"
+    # the population buffers are whole again when they are asked for (mailboxes drained), and stepping goes on
+    for c in cs:
+        c.get_populations()
+    one.step(4)
+    ref = one.get_fields()
+    import torch
+
+    from lattice_boltzmann_method_gpu_b200 import slab
+
+    def view(c, side):
+        s_, r_, ns, nr = c.halo_buffers(side)
+        it = c.dtype.itemsize
+        mk = lambda p, nb: torch.as_tensor(slab._DevBuf(p, max(nb, it), c.dtype), device="cuda")[: nb // it]
+        return (mk(s_, ns), mk(r_, nr)) if s_ else (None, None)
+
+    for it in range(4):
+        for c in cs:
+            c.step_begin(L.STEP_MOMENTS)
+        bufs = [(view(c, 0), view(c, 1)) for c in cs]
+        for c in cs:
+            c.step_interior()
+            c.sync()
+        for r in range(P - 1):
+            (_, _), (s_hi, r_hi) = bufs[r]
+            (s_lo, r_lo), _ = bufs[r + 1]
+            r_lo.copy_(s_hi)
+            r_hi.copy_(s_lo)
+        torch.cuda.synchronize()
+        for c in cs:
+            c.step_end()
+    for k in range(4):
+        got = np.concatenate([c.get_fields()[k] for c in cs])
+        assert np.array_equal(got, ref[k])

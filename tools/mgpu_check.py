@@ -43,7 +43,9 @@ def main():
         c = slab.SlabCase(d)
         flag = H.bif_flag() if name == "bif" else (H.synthetic_openings_mask()[0] if name == "cor" else None)
         c.setup(flag=flag, bc_planes=H.bif_bc_planes() if name == "bif" else None)
-        if os.environ.get("LBM_P2P") == "1" or storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
+        if os.environ.get("LBM_STAGED") == "1" and storage == L.STORE_DENSE_AA:
+            c.enable_staged()  # in-place storage over NCCL send/recv: no peer mapping (lbm_mail_stage)
+        elif os.environ.get("LBM_P2P") == "1" or storage in (L.STORE_DENSE_AA, L.STORE_SPARSE_AA):
             assert c.enable_p2p(), f"peer mapping unavailable: {c.p2p_error}"
         c.step(steps)
         if c._p2p and name == "ldc":  # the multi-process convergence loop: S all-reduced per batch (ldc.cu:653-685)
