@@ -126,9 +126,7 @@ struct Solver final : SolverBase {
     int step_flags = 0;
     // host
     std::vector<int32_t> h_flag;  // global Cartesian, optional
-    std::vector<uint8_t> h_flag_slab;  // (unused since lbm_set_flag_slab uploads at once)
     bool flag_on_device = false;       // d_flag holds the planes lbm_set_flag_slab was given
-    int slab_z0 = 0, slab_nz = 0;
     std::vector<float> h_in, h_out;
     // device
     uint8_t *d_flag = nullptr;
@@ -298,7 +296,6 @@ struct Solver final : SolverBase {
     int set_flag(const int32_t *flag) override {
         if (!flag) FAIL(LBM_ERR_ARG, "null flag");
         h_flag.assign(flag, flag + (size_t)d.nx * d.ny * d.nz);
-        h_flag_slab.clear();
         flag_on_device = false;
         have_flag = true;
         return 0;
@@ -317,7 +314,7 @@ struct Solver final : SolverBase {
         CK(cudaMemcpy2DAsync(d_flag, (size_t)ext.px, flag + (size_t)d.nx * (size_t)d.ny * (size_t)(ext.z0 - z_first), (size_t)d.nx,
                              (size_t)d.nx, (size_t)d.ny * (size_t)(ext.z1 - ext.z0), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
-        h_flag_slab.clear(), h_flag.clear();
+        h_flag.clear();
         flag_on_device = true;
         have_flag = true;
         return 0;
