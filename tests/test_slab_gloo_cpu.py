@@ -8,7 +8,9 @@ neighbour's into the halo planes.  Two gloo ranks must reproduce the single-doma
 
 The second half does the same for the in-place (AA) storage, whose slabs exchange by peer stores on the
 GPU: even steps leave the crossing populations in the neighbour's halo plane, odd steps push them into
-its outermost owned plane (shifted in-plane) -- here carried by the same gloo send/recv."""
+its outermost owned plane (shifted in-plane) -- here carried by the same gloo send/recv, which is also how the
+library moves them between GPUs that cannot map each other's memory (lbm_mail_stage + SlabCase.enable_staged:
+staging planes sent with torch.distributed, merged on arrival; tests/test_slab_gpu.py checks that path on the GPU)."""
 import os
 import socket
 import sys
